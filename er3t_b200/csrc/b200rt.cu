@@ -1,0 +1,1346 @@
+// b200rt.cu -- sm_100a photon-transport solver behind the C-ABI of include/b200rt.h.
+//
+// Replaces the external MCARaTS process that er3t launches at er3t/rtm/mca/mca_run.py:110-113,179-181.
+// Kernels (DESIGN.md has the roofline of each):
+//   pack_scene_kernel      per-voxel total extinction + (omega, apf) records        (HBM streaming)
+//   majorant_kernel        super-voxel majorant grid                                (HBM streaming)
+//   tau_up_kernel          optical depth from each voxel to the top of the 3-D block (vertical local estimates)
+//   transport_kernel       persistent-thread photon transport with in-place regeneration, Philox streams,
+//                          super-voxel DDA + null-collision tracking, local-estimate radiance, fp64 tallies
+//   check_finite_kernel    NaN/Inf guard over the tallies
+// No CPU fallback exists: every entry point fails with an error code if CUDA fails.
+
+#include "../../include/b200rt.h"
+#include "rt_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define MAX_SENS 16
+
+// ============================================================================ device structs
+struct DevSensor {
+    float3 s;            // direction of photon travel toward the sensor (= -viewing vector)
+    float inv_sz;        // 1 / |s.z|
+    float zt;            // target level of the transmittance integral: clamp(zloc, z0, ztoa)
+    float zref;
+    int lt;              // layer that contains zt (nz-1 when zt == ztoa)
+    int nxr, nyr;
+    int vertical_up;     // s == (0,0,1): precomputed tau-to-top table applies in 3-D mode
+    int fast_ok;         // zt is at/above the top of the 3-D block
+    long long off;       // offset of this sensor inside a radiance slab
+};
+
+struct DevJob {
+    unsigned long long first;   // prefix sum of local photon counts
+    unsigned long long count;   // photons of this job handled by this GPU
+    unsigned long long seed;
+    double norm;                // mu0 * src_flx / nphot(job, all GPUs)
+    double rad_scale;
+    int slab;
+    int has_abs;
+    int has_fscale;
+    int _pad;
+};
+
+struct DevStats {
+    unsigned long long photons, n_cell, n_tent, n_coll, n_sfc, n_le, n_le_visit, n_tally, n_kill;
+    double w_toa, w_sfc, w_atm, w_rr;
+};
+
+struct DevScene {
+    int nx, ny, nz, iz0, nz3, np1d, np3d;
+    float dx, dy, Lx, Ly, inv_dx, inv_dy;
+    int svx, svy, svz, ncx, ncy, ncz;
+    float Sx, Sy, inv_Sx, inv_Sy;
+    int nslab_z;
+    // small 1-D tables (global copies; staged into shared memory by the transport kernel)
+    const float* zgrd;        // [nz+1]
+    const float* e1tot;       // [nz]
+    const float* e1cum;       // [nz+1]
+    const float* e1;          // [np1d][nz]
+    const float* o1;          // [np1d][nz]
+    const float* a1;          // [np1d][nz]
+    const int* slab_lay0;     // [nslab_z+1]
+    const int* slab_cz;       // [nslab_z]
+    const float* slab_maj1d;  // [nslab_z]
+    // 3-D block in HBM
+    const float* ext3tot;     // [nz3][ny][nx]
+    const float2* prop3;      // [np3d][nz3][ny][nx]  (omega, apf)
+    const float* ext3;        // [np3d][nz3][ny][nx]  (only read when np3d > 1)
+    const float* maj;         // [ncz][ncy][ncx]
+    const float* tu3;         // [nz3+1][ny][nx]
+    PhaseTab pt;
+    int sfc_nx, sfc_ny;
+    const int* sfc_type;
+    const float* sfc_param;   // [5][sfc_ny][sfc_nx]
+    float3 src;
+    float src_cos_half, mu0;
+    int nrad;
+    DevSensor sens[MAX_SENS];
+    long long rad_slab;       // doubles per radiance slab
+    int solver, target;
+    float wmin, wfac;
+    int iso_ss, iso_max;
+    int shard_rank, shard_world;
+    // jobs
+    int njob;
+    const DevJob* jobs;
+    const float* job_abs;     // [njob][nz]
+    const float* job_cabs;    // [njob][nz+1]
+    const double* job_fscale; // [njob][nz+1]
+    unsigned long long nphot_local;
+    // outputs
+    double* flux;
+    double* rad;
+    double* heat;
+    unsigned long long* counter;
+    DevStats* stats;
+};
+
+// ============================================================================ setup kernels
+__global__ void pack_scene_kernel(const float* __restrict__ ext, const float* __restrict__ omg,
+                                  const float* __restrict__ apf, int np3d, size_t nvox,
+                                  float* __restrict__ ext3tot, float2* __restrict__ prop3, int* __restrict__ bad) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+        float tot = 0.0f;
+        for (int k = 0; k < np3d; ++k) {
+            const float e = ext[size_t(k) * nvox + v];
+            const float o = omg[size_t(k) * nvox + v];
+            const float a = apf[size_t(k) * nvox + v];
+            if (!(e >= 0.0f) || !(o >= 0.0f && o <= 1.0f) || !isfinite(a)) atomicOr(bad, 1);
+            tot += e;
+            prop3[size_t(k) * nvox + v] = make_float2(o, a);
+        }
+        ext3tot[v] = tot;
+    }
+}
+
+__global__ void majorant_kernel(const float* __restrict__ ext3tot, int nx, int ny, int nz3, int svx, int svy, int svz,
+                                int ncx, int ncy, int ncz, float* __restrict__ maj) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncx * ncy * ncz) return;
+    const int cix = c % ncx, ciy = (c / ncx) % ncy, ciz = c / (ncx * ncy);
+    float m = 0.0f;
+    for (int kz = ciz * svz; kz < min(nz3, (ciz + 1) * svz); ++kz)
+        for (int ky = ciy * svy; ky < min(ny, (ciy + 1) * svy); ++ky)
+            for (int kx = cix * svx; kx < min(nx, (cix + 1) * svx); ++kx)
+                m = fmaxf(m, ext3tot[(size_t(kz) * ny + ky) * nx + kx]);
+    maj[c] = m;
+}
+
+__global__ void tau_up_kernel(const float* __restrict__ ext3tot, const float* __restrict__ zgrd, int iz0, int nx, int ny,
+                              int nz3, float* __restrict__ tu3) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nxy = size_t(nx) * ny;
+    if (col >= nxy) return;
+    float acc = 0.0f;
+    tu3[size_t(nz3) * nxy + col] = 0.0f;
+    for (int k = nz3 - 1; k >= 0; --k) {
+        acc += ext3tot[size_t(k) * nxy + col] * (zgrd[iz0 + k + 1] - zgrd[iz0 + k]);
+        tu3[size_t(k) * nxy + col] = acc;
+    }
+}
+
+__global__ void check_finite_kernel(const double* __restrict__ a, size_t n, int* __restrict__ bad) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    int b = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (!isfinite(a[i])) b = 1;
+    if (b) atomicOr(bad, 1);
+}
+
+// ============================================================================ transport kernel
+struct Smem {
+    const float* z;       // [nz+1]
+    const float* e1tot;   // [nz]
+    const float* e1cum;   // [nz+1]
+    const float* e1;      // [np1d][nz]
+    const float* o1;
+    const float* a1;
+    const int* lay0;      // [nslab_z+1]
+    const int* cz;        // [nslab_z]
+    const float* maj1d;   // [nslab_z]
+};
+
+struct Photon {
+    float x, y, z;
+    float3 d;
+    float w;
+    float tau;
+    int cix, ciy;     // coarse cell (3-D slabs) -- the column itself when frozen
+    int is;           // z slab
+    int iz;           // layer
+    int order;
+    int job;
+    bool direct, frozen;
+};
+
+__device__ __forceinline__ float wrapf(float x, float L) {
+    x -= L * floorf(x / L);
+    if (x >= L) x = 0.0f;
+    if (x < 0.0f) x = 0.0f;
+    return x;
+}
+
+__device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
+
+__device__ __forceinline__ void flux_tally(const DevScene& S, const DevJob& J, const Photon& p, int var, int lev,
+                                           unsigned& n_tally) {
+    int fx, fy;
+    if (p.frozen) { fx = p.cix; fy = p.ciy; }
+    else {
+        fx = min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+        fy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+    }
+    const size_t nxy = size_t(S.nx) * S.ny;
+    double sc = J.norm * double(nxy);
+    if (J.has_fscale) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + lev);
+    tally_add(S.flux + ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx, double(p.w) * sc);
+    ++n_tally;
+}
+
+// gas-absorption optical depth of a straight segment inside one z slab
+__device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int job, float za, int iza, float zb, int izb,
+                                         float dist, float inv_absdz) {
+    const float* ab = S.job_abs + size_t(job) * S.nz;
+    if (iza == izb) return __ldg(ab + iza) * dist;
+    const float* cb = S.job_cabs + size_t(job) * (S.nz + 1);
+    const float ca = __ldg(cb + iza) + __ldg(ab + iza) * (za - sm.z[iza]);
+    const float c2 = __ldg(cb + izb) + __ldg(ab + izb) * (zb - sm.z[izb]);
+    return fabsf(c2 - ca) * inv_absdz;
+}
+
+// Optical depth (extinction + gas absorption) from (x,y,z) along sensor direction to the sensor's target level.
+// fx, fy: fine column if the start point lies in a 3-D layer (else recomputed); s3: 3-D extinction of the start voxel.
+__device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs, int fx, int fy,
+                        float s3, unsigned& n_visit) {
+    const float* ab = S.job_abs + size_t(p.job) * S.nz;
+    const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
+    const int iz = p.iz;
+    const size_t nxy = size_t(S.nx) * S.ny;
+    const bool in3 = (S.nz3 > 0) && iz >= S.iz0 && iz < S.iz0 + S.nz3;
+    if (se.fast_ok && se.s.z > 0.0f && (p.frozen || se.vertical_up)) {
+        // ---- vertical (or column-frozen) fast path: O(1) look-ups in the precomputed tables
+        float t1 = (sm.e1cum[se.lt] + sm.e1tot[se.lt] * (se.zt - sm.z[se.lt])) - (sm.e1cum[iz] + sm.e1tot[iz] * (p.z - sm.z[iz]));
+        if (has_abs) t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
+        if (S.nz3 > 0 && iz < S.iz0 + S.nz3) {
+            if (!in3) {
+                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                t1 += __ldg(S.tu3 + size_t(fy) * S.nx + fx);
+            } else {
+                t1 += __ldg(S.tu3 + size_t(iz - S.iz0 + 1) * nxy + size_t(fy) * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
+            }
+            ++n_visit;
+        }
+        return fmaxf(0.0f, t1) * se.inv_sz;
+    }
+    // ---- generic path: exact traversal, layer by layer, column by column inside the 3-D block
+    float tau = 0.0f;
+    float x = p.x, y = p.y, z = p.z;
+    int l = iz;
+    const bool up = se.s.z > 0.0f;
+    if (up && z >= sm.z[l + 1] && l + 1 < S.nz) l++;
+    if (!up && z <= sm.z[l] && l > 0) l--;
+    bool have_col = in3 && (l == iz);
+    if (p.frozen) { fx = p.cix; fy = p.ciy; have_col = true; }
+    const float isx = se.s.x != 0.0f ? 1.0f / se.s.x : RT_INF;
+    const float isy = se.s.y != 0.0f ? 1.0f / se.s.y : RT_INF;
+    const float isz = 1.0f / se.s.z;
+    for (;;) {
+        const float zb = up ? fminf(sm.z[l + 1], se.zt) : fmaxf(sm.z[l], se.zt);
+        const float dl = fmaxf(0.0f, (zb - z) * isz);
+        const float base = sm.e1tot[l] + (has_abs ? __ldg(ab + l) : 0.0f);
+        const bool l3 = (S.nz3 > 0) && l >= S.iz0 && l < S.iz0 + S.nz3;
+        if (!l3) {
+            tau += base * dl;
+            if (!p.frozen) { x = wrapf(x + se.s.x * dl, S.Lx); y = wrapf(y + se.s.y * dl, S.Ly); }
+            have_col = p.frozen;
+        } else if (p.frozen) {
+            tau += (base + __ldg(S.ext3tot + size_t(l - S.iz0) * nxy + size_t(fy) * S.nx + fx)) * dl;
+            ++n_visit;
+        } else {
+            if (!have_col) {
+                fx = min(S.nx - 1, max(0, int(x * S.inv_dx)));
+                fy = min(S.ny - 1, max(0, int(y * S.inv_dy)));
+                have_col = true;
+            }
+            float rem = dl;
+            for (;;) {
+                float tx = RT_INF, ty = RT_INF;
+                if (se.s.x > 0.0f) tx = (float(fx + 1) * S.dx - x) * isx; else if (se.s.x < 0.0f) tx = (float(fx) * S.dx - x) * isx;
+                if (se.s.y > 0.0f) ty = (float(fy + 1) * S.dy - y) * isy; else if (se.s.y < 0.0f) ty = (float(fy) * S.dy - y) * isy;
+                tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
+                const float step = fminf(rem, fminf(tx, ty));
+                tau += (base + __ldg(S.ext3tot + size_t(l - S.iz0) * nxy + size_t(fy) * S.nx + fx)) * step;
+                ++n_visit;
+                if (step >= rem) { x += se.s.x * rem; y += se.s.y * rem; break; }
+                rem -= step;
+                x += se.s.x * step; y += se.s.y * step;
+                if (tx <= ty) {
+                    if (se.s.x > 0.0f) { fx++; x = float(fx) * S.dx; if (fx >= S.nx) { fx = 0; x = 0.0f; } }
+                    else { x = float(fx) * S.dx; fx--; if (fx < 0) { fx = S.nx - 1; x = S.Lx; } }
+                } else {
+                    if (se.s.y > 0.0f) { fy++; y = float(fy) * S.dy; if (fy >= S.ny) { fy = 0; y = 0.0f; } }
+                    else { y = float(fy) * S.dy; fy--; if (fy < 0) { fy = S.ny - 1; y = S.Ly; } }
+                }
+            }
+        }
+        z = zb;
+        if (up) { if (zb >= se.zt || l + 1 >= S.nz) break; l++; }
+        else { if (zb <= se.zt || l == 0) break; l--; }
+    }
+    return tau;
+}
+
+// deposit one local-estimate contribution (f = angular density toward the sensor, 1/sr, already times weight)
+__device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevJob& J, const DevSensor& se,
+                                           const Photon& p, float fw, int fx, int fy, float s3, unsigned& n_le,
+                                           unsigned& n_visit, unsigned& n_tally) {
+    const float tau = le_tau(S, sm, se, p, J.has_abs, fx, fy, s3, n_visit);
+    ++n_le;
+    const float contrib = fw * __expf(-tau) * se.inv_sz;
+    int px, py;
+    if (p.frozen) {
+        px = min(se.nxr - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(se.nxr)));
+        py = min(se.nyr - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(se.nyr)));
+    } else {
+        const float t = (se.zref - p.z) / se.s.z;
+        const float xr = wrapf(p.x + se.s.x * t, S.Lx), yr = wrapf(p.y + se.s.y * t, S.Ly);
+        px = min(se.nxr - 1, max(0, int(xr / S.Lx * float(se.nxr))));
+        py = min(se.nyr - 1, max(0, int(yr / S.Ly * float(se.nyr))));
+    }
+    tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + size_t(py) * se.nxr + px,
+              double(contrib) * J.norm * J.rad_scale * double(se.nxr) * double(se.nyr));
+    ++n_tally;
+}
+
+__global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ DevScene S) {
+    extern __shared__ float smem_f[];
+    // ---- stage the 1-D tables into shared memory
+    Smem sm;
+    {
+        float* q = smem_f;
+        float* z = q; q += S.nz + 1;
+        float* e1tot = q; q += S.nz;
+        float* e1cum = q; q += S.nz + 1;
+        float* e1 = q; q += S.np1d * S.nz;
+        float* o1 = q; q += S.np1d * S.nz;
+        float* a1 = q; q += S.np1d * S.nz;
+        float* maj1d = q; q += S.nslab_z;
+        int* lay0 = reinterpret_cast<int*>(q); q += S.nslab_z + 1;
+        int* cz = reinterpret_cast<int*>(q);
+        for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
+        for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
+        for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
+        for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) { maj1d[i] = S.slab_maj1d[i]; cz[i] = S.slab_cz[i]; }
+        for (int i = threadIdx.x; i <= S.nslab_z; i += blockDim.x) lay0[i] = S.slab_lay0[i];
+        sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
+        sm.maj1d = maj1d; sm.lay0 = lay0; sm.cz = cz;
+    }
+    __syncthreads();
+
+    const bool want_flux = (S.target & B200RT_TARGET_FLUX) != 0;
+    const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
+    const bool want_heat = (S.target & B200RT_TARGET_HEATING) != 0;
+    const size_t nxy = size_t(S.nx) * S.ny;
+
+    unsigned n_cell = 0, n_tent = 0, n_coll = 0, n_sfc = 0, n_le = 0, n_visit = 0, n_tally = 0, n_kill = 0, n_phot = 0;
+    double w_toa = 0.0, w_sfc = 0.0, w_atm = 0.0, w_rr = 0.0;
+
+    Photon p;
+    Philox4 g;
+    DevJob J;
+    float3 invd = make_float3(0.f, 0.f, 0.f);
+    bool alive = false;
+    p.job = -1;
+    g.c3 = 0xB200u;
+
+    for (;;) {
+        if (!alive) {
+            // ---- regeneration: warp-aggregated fetch of the next photon index
+            const unsigned mask = __activemask();
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(S.counter, (unsigned long long)__popc(mask));
+            base = __shfl_sync(mask, base, leader);
+            const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1u));
+            if (idx >= S.nphot_local) break;
+            // job look-up (jobs are few; binary search on the prefix sums)
+            int lo = 0, hi = S.njob - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+            }
+            if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
+            const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
+            g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
+            g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
+            const float4 u = rng4(g);
+            const float4 v = rng4(g);
+            p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
+            if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
+            else p.d = S.src;
+            p.w = 1.0f; p.order = 0; p.direct = true;
+            p.is = S.nslab_z - 1; p.iz = S.nz - 1;
+            p.frozen = (S.solver == B200RT_SOLVER_IPA);
+            p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
+            p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
+            if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
+            p.tau = -__logf(v.x);
+            invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
+            invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
+            invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
+            alive = true;
+            ++n_phot;
+            if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
+        }
+
+        // ---- one event step inside the current cell
+        const int is = p.is;
+        const int l0 = sm.lay0[is], l1 = sm.lay0[is + 1];
+        const float zlo = sm.z[l0], zhi = sm.z[l1];
+        const int cz = sm.cz[is];
+        const bool in3 = cz >= 0;
+        float M = sm.maj1d[is];
+        float tz = RT_INF, tx = RT_INF, ty = RT_INF;
+        if (p.d.z > 0.0f) tz = (zhi - p.z) * invd.z; else if (p.d.z < 0.0f) tz = (zlo - p.z) * invd.z;
+        if (in3) {
+            M += __ldg(S.maj + (size_t(cz) * S.ncy + p.ciy) * S.ncx + p.cix);
+            ++n_cell;
+            if (!p.frozen) {
+                if (p.d.x > 0.0f) tx = (fminf(float(p.cix + 1) * S.Sx, S.Lx) - p.x) * invd.x;
+                else if (p.d.x < 0.0f) tx = (float(p.cix) * S.Sx - p.x) * invd.x;
+                if (p.d.y > 0.0f) ty = (fminf(float(p.ciy + 1) * S.Sy, S.Ly) - p.y) * invd.y;
+                else if (p.d.y < 0.0f) ty = (float(p.ciy) * S.Sy - p.y) * invd.y;
+            }
+        }
+        tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
+        const float dexit = fminf(tz, fminf(tx, ty));
+        const float dcol = M > 0.0f ? p.tau / M : RT_INF;
+        const float inv_absdz = fabsf(invd.z);
+
+        if (dcol < dexit) {
+            // ================= tentative collision
+            const float zn = p.z + p.d.z * dcol;
+            int izn = p.iz;
+            if (l1 - l0 > 1) {
+                izn = l0;
+                while (izn < l1 - 1 && zn >= sm.z[izn + 1]) ++izn;
+            }
+            if (J.has_abs) {
+                const float ta = abs_tau(S, sm, p.job, p.z, p.iz, zn, izn, dcol, inv_absdz);
+                const float wn = p.w * __expf(-ta);
+                w_atm += double(p.w) - double(wn);
+                if (want_heat) {
+                    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
+                              (double(p.w) - double(wn)) * J.norm * double(nxy));
+                    ++n_tally;
+                }
+                p.w = wn;
+            }
+            if (!p.frozen) {
+                p.x += p.d.x * dcol; p.y += p.d.y * dcol;
+                if (!in3) { p.x = wrapf(p.x, S.Lx); p.y = wrapf(p.y, S.Ly); }
+            }
+            p.z = zn; p.iz = izn;
+            const float4 u = rng4(g);
+            float sig = sm.e1tot[izn];
+            float s3 = 0.0f;
+            int fx = 0, fy = 0;
+            size_t vox = 0;
+            if (in3) {
+                if (p.frozen) { fx = p.cix; fy = p.ciy; }
+                else {
+                    fx = min(min(S.nx, (p.cix + 1) * S.svx) - 1, max(p.cix * S.svx, int(p.x * S.inv_dx)));
+                    fy = min(min(S.ny, (p.ciy + 1) * S.svy) - 1, max(p.ciy * S.svy, int(p.y * S.inv_dy)));
+                }
+                vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                s3 = __ldg(S.ext3tot + vox);
+                sig += s3;
+                ++n_tent;
+            }
+            p.tau = -__logf(u.y);
+            float uc = u.x * M;
+            if (uc < sig) {
+                // ============= real collision: pick the scattering component (uc is uniform on [0, sig))
+                float omg = 1.0f, apf = 0.0f;
+                bool found = false;
+                if (uc < s3) {
+                    if (S.np3d == 1) {
+                        const float2 pr = __ldg(S.prop3 + vox);
+                        omg = pr.x; apf = pr.y; found = true;
+                    } else {
+                        const size_t n3 = size_t(S.nz3) * nxy;
+                        for (int k = 0; k < S.np3d; ++k) {
+                            const float e = __ldg(S.ext3 + size_t(k) * n3 + vox);
+                            if (uc < e || k == S.np3d - 1) {
+                                const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + vox);
+                                omg = pr.x; apf = pr.y; found = true;
+                                break;
+                            }
+                            uc -= e;
+                        }
+                    }
+                } else uc -= s3;
+                if (!found) {
+                    for (int k = 0; k < S.np1d; ++k) {
+                        const float e = sm.e1[k * S.nz + izn];
+                        if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
+                        uc -= e;
+                    }
+                }
+                ++n_coll;
+                const float wn = p.w * omg;
+                if (wn < p.w) {
+                    w_atm += double(p.w) - double(wn);
+                    if (want_heat) {
+                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                        tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
+                                  (double(p.w) - double(wn)) * J.norm * double(nxy));
+                        ++n_tally;
+                    }
+                }
+                p.w = wn;
+                p.order++; p.direct = false;
+                if (!(p.w > 0.0f)) { alive = false; continue; }
+                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                    if (!in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
+                    else { p.cix = fx; p.ciy = fy; }
+                    p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                    p.frozen = true;
+                }
+                if (want_rad) {
+                    for (int k = 0; k < S.nrad; ++k) {
+                        const DevSensor& se = S.sens[k];
+                        const float dzs = (se.zt - p.z) * se.s.z;
+                        if (!(dzs > 0.0f)) continue;
+                        const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
+                        const float f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
+                        if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
+                    }
+                }
+                float xi_tab = 0.5f;
+                if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
+                const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
+                p.d = rotate_dir(p.d, mu, RT_2PI * u.w);
+                invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
+                invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
+                invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
+                if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
+                if (p.w < S.wmin) {
+                    const float4 v = rng4(g);
+                    if (v.x * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
+                    else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
+                }
+                if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
+            }
+        } else {
+            // ================= move to the cell boundary
+            p.tau = fmaxf(0.0f, p.tau - M * dexit);
+            const bool zcross = (tz <= tx && tz <= ty);
+            float zn = p.z + p.d.z * dexit;
+            int izn = p.iz;
+            if (zcross) { zn = p.d.z > 0.0f ? zhi : zlo; izn = p.d.z > 0.0f ? l1 - 1 : l0; }
+            else if (l1 - l0 > 1) { izn = l0; while (izn < l1 - 1 && zn >= sm.z[izn + 1]) ++izn; }
+            if (J.has_abs) {
+                const float ta = abs_tau(S, sm, p.job, p.z, p.iz, zn, izn, dexit, inv_absdz);
+                const float wn = p.w * __expf(-ta);
+                w_atm += double(p.w) - double(wn);
+                if (want_heat) {
+                    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
+                              (double(p.w) - double(wn)) * J.norm * double(nxy));
+                    ++n_tally;
+                }
+                p.w = wn;
+            }
+            if (!p.frozen) {
+                p.x += p.d.x * dexit; p.y += p.d.y * dexit;
+                if (!in3) { p.x = wrapf(p.x, S.Lx); p.y = wrapf(p.y, S.Ly); }
+            }
+            p.z = zn; p.iz = izn;
+            if (zcross) {
+                if (p.d.z > 0.0f) {
+                    if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
+                    if (is + 1 >= S.nslab_z) { w_toa += double(p.w); alive = false; continue; }
+                    p.is = is + 1; p.iz = l1;
+                } else {
+                    if (want_flux) {
+                        if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
+                        flux_tally(S, J, p, 1, l0, n_tally);
+                    }
+                    if (is > 0) { p.is = is - 1; p.iz = l0 - 1; }
+                }
+                if (is > 0 || p.d.z > 0.0f) {
+                    // entering a 3-D slab from a 1-D slab: locate the coarse cell
+                    if (!in3 && sm.cz[p.is] >= 0 && !p.frozen) {
+                        p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                        p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+                    }
+                } else {
+                    // ============= surface
+                    ++n_sfc;
+                    int sx, sy;
+                    if (p.frozen) {
+                        sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
+                        sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
+                    } else {
+                        sx = min(S.sfc_nx - 1, max(0, int(p.x / S.Lx * float(S.sfc_nx))));
+                        sy = min(S.sfc_ny - 1, max(0, int(p.y / S.Ly * float(S.sfc_ny))));
+                    }
+                    const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
+                    const int type = __ldg(S.sfc_type + si);
+                    float prm[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
+                    const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
+                    if (want_rad) {
+                        int fx = 0, fy = 0;
+                        float s3 = 0.0f;
+                        if (S.nz3 > 0 && S.iz0 == 0) {
+                            fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                            fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                            s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
+                        }
+                        for (int k = 0; k < S.nrad; ++k) {
+                            const DevSensor& se = S.sens[k];
+                            if (!(se.s.z > 0.0f) || !(se.zt > p.z)) continue;
+                            const float f = brdf_eval(type, prm, wi, se.s) * se.s.z;
+                            if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
+                        }
+                    }
+                    const float4 u = rng4(g);
+                    float3 wo = make_float3(0.f, 0.f, 1.f);
+                    float fac = 0.0f;
+                    bool diffuse = true;
+                    if (type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
+                    if (diffuse) {
+                        const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
+                        float sp, cp;
+                        __sincosf(RT_2PI * u.y, &sp, &cp);
+                        wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
+                        fac = (type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
+                    } else {
+                        const float sig2 = fmaxf(1e-6f, prm[4]);
+                        const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
+                        float sp, cp;
+                        __sincosf(RT_2PI * u.y, &sp, &cp);
+                        const float zx = r * cp, zy = r * sp;
+                        const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
+                        const float3 n = make_float3(-zx * nn, -zy * nn, nn);
+                        const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
+                        if (cosg > 0.0f) {
+                            wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
+                            if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
+                        }
+                    }
+                    const float wn = p.w * fac;
+                    w_sfc += double(p.w) - double(wn);
+                    p.w = wn;
+                    if (!(p.w > 0.0f)) { alive = false; continue; }
+                    {
+                        const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
+                        p.d = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
+                    }
+                    invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
+                    invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
+                    invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
+                    p.direct = false; p.order++;
+                    p.is = 0; p.iz = 0; p.z = sm.z[0];
+                    if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
+                    if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                        p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                        p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                        p.frozen = true;
+                    }
+                    if (p.w < S.wmin) {
+                        if (u.w * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
+                        else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
+                    }
+                    if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
+                }
+            } else if (tx <= ty) {
+                if (p.d.x > 0.0f) { if (p.cix + 1 >= S.ncx) { p.cix = 0; p.x = 0.0f; } else { p.cix++; p.x = float(p.cix) * S.Sx; } }
+                else { p.x = float(p.cix) * S.Sx; p.cix--; if (p.cix < 0) { p.cix = S.ncx - 1; p.x = S.Lx; } }
+            } else {
+                if (p.d.y > 0.0f) { if (p.ciy + 1 >= S.ncy) { p.ciy = 0; p.y = 0.0f; } else { p.ciy++; p.y = float(p.ciy) * S.Sy; } }
+                else { p.y = float(p.ciy) * S.Sy; p.ciy--; if (p.ciy < 0) { p.ciy = S.ncy - 1; p.y = S.Ly; } }
+            }
+        }
+    }
+
+    // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
+    unsigned long long c[9] = {n_phot, n_cell, n_tent, n_coll, n_sfc, n_le, n_visit, n_tally, n_kill};
+    double dsum[4] = {w_toa, w_sfc, w_atm, w_rr};
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        unsigned long long v = c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        c[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double v = dsum[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        dsum[i] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* sc = reinterpret_cast<unsigned long long*>(S.stats);
+        for (int i = 0; i < 9; ++i) if (c[i]) atomicAdd(sc + i, c[i]);
+        atomicAdd(&S.stats->w_toa, dsum[0]); atomicAdd(&S.stats->w_sfc, dsum[1]);
+        atomicAdd(&S.stats->w_atm, dsum[2]); atomicAdd(&S.stats->w_rr, dsum[3]);
+    }
+}
+
+// ============================================================================ test-hook kernels
+__global__ void philox_fill_kernel(unsigned long long seed, unsigned long long first, unsigned c2, unsigned c3, uint4* out,
+                                   long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long idx = first + (unsigned long long)i;
+    out[i] = philox4x32_10(unsigned(idx), unsigned(idx >> 32), c2, c3, unsigned(seed), unsigned(seed >> 32));
+}
+__global__ void phase_eval_kernel(PhaseTab pt, float apf, const double* mu, double* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = double(phase_eval(pt, apf, float(mu[i])));
+}
+__global__ void phase_sample_kernel(PhaseTab pt, float apf, const double* xi, double* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = double(phase_sample(pt, apf, float(xi[i]), 0.999999f));
+}
+__global__ void brdf_eval_kernel(int type, const float* prm5, const double* din, const double* dout, double* f, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[5];
+    for (int q = 0; q < 5; ++q) p[q] = prm5[q];
+    const float3 wi = make_float3(-float(din[3 * i]), -float(din[3 * i + 1]), -float(din[3 * i + 2]));
+    const float3 wo = make_float3(float(dout[3 * i]), float(dout[3 * i + 1]), float(dout[3 * i + 2]));
+    f[i] = double(brdf_eval(type, p, wi, wo));
+}
+
+// ============================================================================ host side
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct Handle {
+    int device = 0;
+    std::string err;
+    bool have_scene = false;
+    DevScene S{};
+    b200rt_options opt{};
+    int numSM = 0;
+    size_t smem_bytes = 0;
+    // owned device memory
+    std::vector<DevBuf*> pool;
+    DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d;
+    DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
+    DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
+    DevBuf flux, rad, heat;
+    size_t nflux = 0, nrad = 0, nheat = 0;
+    std::vector<float> h_zgrd;
+    double src_flx = 1.0;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    b200rt_stats stats_host{};
+    bool ran = false;
+    uint64_t launches = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            H->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + #call;              \
+            return B200RT_ERR_CUDA;                                                                      \
+        }                                                                                                \
+    } while (0)
+
+int fail(Handle* H, int code, const std::string& msg) {
+    H->err = msg;
+    return code;
+}
+
+int dev_alloc(Handle* H, DevBuf& b, size_t bytes) {
+    if (b.p && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096) return 0;
+    b.release();
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        H->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        b.p = nullptr;
+        return B200RT_ERR_NOMEM;
+    }
+    b.bytes = bytes;
+    return 0;
+}
+
+template <class T>
+int upload(Handle* H, DevBuf& b, const std::vector<T>& v) {
+    int rc = dev_alloc(H, b, v.size() * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// copy `n` elements from a host-or-device pointer into a host vector
+template <class T>
+int fetch_host(Handle* H, const T* src, size_t n, std::vector<T>& out) {
+    out.resize(n);
+    if (n == 0) return 0;
+    if (!src) return fail(H, B200RT_ERR_ARG, "null pointer in scene");
+    CK(cudaMemcpy(out.data(), src, n * sizeof(T), cudaMemcpyDefault));
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+float3 dir_from_angles(double the, double phi) {
+    const double t = the * M_PI / 180.0, p = phi * M_PI / 180.0;
+    double x = std::sin(t) * std::cos(p), y = std::sin(t) * std::sin(p), z = std::cos(t);
+    if (std::fabs(x) < 1e-15) x = 0;
+    if (std::fabs(y) < 1e-15) y = 0;
+    return make_float3(float(x), float(y), float(z));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rt_version(void) { return B200RT_VERSION; }
+
+int b200rt_create(void** handle, int device) {
+    if (!handle) return B200RT_ERR_ARG;
+    *handle = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return B200RT_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return B200RT_ERR_CUDA;
+    Handle* H = new Handle();
+    H->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete H; return B200RT_ERR_CUDA; }
+    H->numSM = prop.multiProcessorCount;
+    cudaEventCreate(&H->ev0);
+    cudaEventCreate(&H->ev1);
+    *handle = H;
+    return B200RT_OK;
+}
+
+int b200rt_destroy(void* handle) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    cudaSetDevice(H->device);
+    DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
+                     &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
+                     &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
+                     &H->flux, &H->rad, &H->heat};
+    for (DevBuf* b : all) b->release();
+    if (H->ev0) cudaEventDestroy(H->ev0);
+    if (H->ev1) cudaEventDestroy(H->ev1);
+    delete H;
+    return B200RT_OK;
+}
+
+const char* b200rt_last_error(void* handle) {
+    Handle* H = static_cast<Handle*>(handle);
+    return H ? H->err.c_str() : "null handle";
+}
+
+int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_options* opt) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!sc || !opt) return fail(H, B200RT_ERR_ARG, "null scene/options");
+    CK(cudaSetDevice(H->device));
+    H->have_scene = false;
+    // ------------------------------------------------ validate
+    if (sc->nx < 1 || sc->ny < 1 || sc->nz < 1 || sc->np1d < 1) return fail(H, B200RT_ERR_ARG, "nx, ny, nz, np1d must be >= 1");
+    if (!(sc->dx > 0) || !(sc->dy > 0)) return fail(H, B200RT_ERR_ARG, "dx, dy must be > 0");
+    const int nz = sc->nz, nz3 = sc->nz3, iz0 = sc->iz3l - 1;
+    if (nz3 < 0 || (nz3 > 0 && (iz0 < 0 || iz0 + nz3 > nz))) return fail(H, B200RT_ERR_ARG, "3-D block [iz3l, iz3l+nz3) exceeds the atmosphere (Atm_iz3l is 1-based)");
+    if (nz3 > 0 && (sc->np3d < 1 || !sc->ext3d || !sc->omg3d || !sc->apf3d)) return fail(H, B200RT_ERR_ARG, "3-D block without fields");
+    if (sc->abs3d) return fail(H, B200RT_ERR_ARG, "Atm_abst3d != 0 is not supported by the CUDA path yet");
+    if (sc->nrad < 0 || sc->nrad > MAX_SENS) return fail(H, B200RT_ERR_ARG, "nrad out of range (max 16)");
+    if (opt->nslab < 1) return fail(H, B200RT_ERR_ARG, "nslab must be >= 1");
+    if (opt->solver < 0 || opt->solver > 2) return fail(H, B200RT_ERR_ARG, "unknown solver mode");
+    if (opt->shard_world < 1 || opt->shard_rank < 0 || opt->shard_rank >= opt->shard_world) return fail(H, B200RT_ERR_ARG, "bad shard rank/world");
+    if (sc->sfc_nx < 1 || sc->sfc_ny < 1 || !sc->sfc_type || !sc->sfc_param) return fail(H, B200RT_ERR_ARG, "surface missing");
+
+    std::vector<double> zg, e1, o1, a1;
+    int rc;
+    if ((rc = fetch_host(H, sc->zgrd, size_t(nz) + 1, zg))) return rc;
+    if ((rc = fetch_host(H, sc->ext1d, size_t(sc->np1d) * nz, e1))) return rc;
+    if ((rc = fetch_host(H, sc->omg1d, size_t(sc->np1d) * nz, o1))) return rc;
+    if ((rc = fetch_host(H, sc->apf1d, size_t(sc->np1d) * nz, a1))) return rc;
+    for (int i = 0; i < nz; ++i) if (!(zg[i + 1] > zg[i])) return fail(H, B200RT_ERR_ARG, "Atm_zgrd0 must be strictly increasing");
+    for (size_t i = 0; i < e1.size(); ++i)
+        if (!(e1[i] >= 0) || !(o1[i] >= 0 && o1[i] <= 1) || !std::isfinite(a1[i])) return fail(H, B200RT_ERR_ARG, "1-D profile out of range (ext >= 0, 0 <= omg <= 1)");
+
+    DevScene& S = H->S;
+    std::memset(&S, 0, sizeof(S));
+    S.nx = sc->nx; S.ny = sc->ny; S.nz = nz; S.iz0 = nz3 > 0 ? iz0 : 0; S.nz3 = nz3; S.np1d = sc->np1d; S.np3d = nz3 > 0 ? sc->np3d : 0;
+    S.dx = float(sc->dx); S.dy = float(sc->dy); S.Lx = float(sc->dx * sc->nx); S.Ly = float(sc->dy * sc->ny);
+    S.inv_dx = float(1.0 / sc->dx); S.inv_dy = float(1.0 / sc->dy);
+    S.solver = opt->solver; S.target = opt->target;
+    S.wmin = float(opt->wmin); S.wfac = float(opt->wfac > 0 ? opt->wfac : 1.0);
+    S.iso_ss = opt->iso_ss > 0 ? opt->iso_ss : 1;
+    S.iso_max = opt->iso_max > 0 ? opt->iso_max : 1000000;
+    S.shard_rank = opt->shard_rank; S.shard_world = opt->shard_world;
+
+    // ------------------------------------------------ super-voxel grid
+    const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0;
+    int svx = opt->svx > 0 ? opt->svx : 4, svy = opt->svy > 0 ? opt->svy : 4, svz = opt->svz > 0 ? opt->svz : (nz3 > 16 ? 4 : 1);
+    if (opt->solver != B200RT_SOLVER_3D) { svx = 1; svy = 1; }     // column-frozen modes need cell == column
+    if (per_level) svz = 1;                                       // every z crossing must be a level crossing
+    svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
+    S.svx = svx; S.svy = svy; S.svz = svz;
+    S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
+    S.Sx = float(sc->dx * svx); S.Sy = float(sc->dy * svy); S.inv_Sx = 1.0f / S.Sx; S.inv_Sy = 1.0f / S.Sy;
+
+    // ------------------------------------------------ 1-D tables
+    std::vector<float> fz(nz + 1), fe1tot(nz, 0.f), fe1cum(nz + 1, 0.f), fe1(e1.size()), fo1(e1.size()), fa1(e1.size());
+    std::vector<double> e1tot_d(nz, 0.0);
+    for (int i = 0; i <= nz; ++i) fz[i] = float(zg[i]);
+    for (int k = 0; k < sc->np1d; ++k)
+        for (int i = 0; i < nz; ++i) {
+            e1tot_d[i] += e1[size_t(k) * nz + i];
+            fe1[size_t(k) * nz + i] = float(e1[size_t(k) * nz + i]);
+            fo1[size_t(k) * nz + i] = float(o1[size_t(k) * nz + i]);
+            fa1[size_t(k) * nz + i] = float(a1[size_t(k) * nz + i]);
+        }
+    {
+        double acc = 0;
+        for (int i = 0; i < nz; ++i) { fe1tot[i] = float(e1tot_d[i]); fe1cum[i] = float(acc); acc += e1tot_d[i] * (zg[i + 1] - zg[i]); }
+        fe1cum[nz] = float(acc);
+    }
+    H->h_zgrd = fz;
+    // z slabs: 1-D layers are their own slab; the 3-D block is cut into ncz slabs of svz layers
+    std::vector<int> lay0, czv;
+    std::vector<float> maj1d;
+    for (int i = 0; i < nz;) {
+        int n = 1, cz = -1;
+        if (nz3 > 0 && i >= iz0 && i < iz0 + nz3) { cz = (i - iz0) / svz; n = std::min(svz, iz0 + nz3 - i); }
+        lay0.push_back(i); czv.push_back(cz);
+        float m = 0.f;
+        for (int q = i; q < i + n; ++q) m = std::max(m, std::nextafter(fe1tot[q], 1e30f));
+        maj1d.push_back(m);
+        i += n;
+    }
+    S.nslab_z = int(czv.size());
+    lay0.push_back(nz);
+    if ((rc = upload(H, H->zgrd, fz)) || (rc = upload(H, H->e1tot, fe1tot)) || (rc = upload(H, H->e1cum, fe1cum)) ||
+        (rc = upload(H, H->e1, fe1)) || (rc = upload(H, H->o1, fo1)) || (rc = upload(H, H->a1, fa1)) ||
+        (rc = upload(H, H->slab_lay0, lay0)) || (rc = upload(H, H->slab_cz, czv)) || (rc = upload(H, H->slab_maj1d, maj1d)))
+        return rc;
+    S.zgrd = (const float*)H->zgrd.p; S.e1tot = (const float*)H->e1tot.p; S.e1cum = (const float*)H->e1cum.p;
+    S.e1 = (const float*)H->e1.p; S.o1 = (const float*)H->o1.p; S.a1 = (const float*)H->a1.p;
+    S.slab_lay0 = (const int*)H->slab_lay0.p; S.slab_cz = (const int*)H->slab_cz.p; S.slab_maj1d = (const float*)H->slab_maj1d.p;
+    H->smem_bytes = sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz + S.nslab_z) + sizeof(int) * (2 * size_t(S.nslab_z) + 1);
+    if (H->smem_bytes > 200 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
+
+    // ------------------------------------------------ 3-D block
+    if (nz3 > 0) {
+        const size_t nvox = size_t(nz3) * sc->ny * sc->nx;
+        const size_t nall = nvox * sc->np3d;
+        if ((rc = dev_alloc(H, H->ext3tot, nvox * 4)) || (rc = dev_alloc(H, H->prop3, nall * 8)) ||
+            (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
+            (rc = dev_alloc(H, H->flag, 16)))
+            return rc;
+        // stage the caller's arrays on the device when they are host pointers
+        DevBuf st_e, st_o, st_a;
+        const float *de = sc->ext3d, *dom = sc->omg3d, *da = sc->apf3d;
+        if (sc->np3d > 1) {
+            if ((rc = dev_alloc(H, H->ext3, nall * 4))) return rc;
+            CK(cudaMemcpy(H->ext3.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
+            de = (const float*)H->ext3.p;
+        } else if (!is_device_ptr(sc->ext3d)) {
+            if ((rc = dev_alloc(H, st_e, nall * 4))) return rc;
+            CK(cudaMemcpy(st_e.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
+            de = (const float*)st_e.p;
+        }
+        if (!is_device_ptr(sc->omg3d)) {
+            if ((rc = dev_alloc(H, st_o, nall * 4))) { st_e.release(); return rc; }
+            CK(cudaMemcpy(st_o.p, sc->omg3d, nall * 4, cudaMemcpyDefault));
+            dom = (const float*)st_o.p;
+        }
+        if (!is_device_ptr(sc->apf3d)) {
+            if ((rc = dev_alloc(H, st_a, nall * 4))) { st_e.release(); st_o.release(); return rc; }
+            CK(cudaMemcpy(st_a.p, sc->apf3d, nall * 4, cudaMemcpyDefault));
+            da = (const float*)st_a.p;
+        }
+        CK(cudaMemset(H->flag.p, 0, 16));
+        const int nb = int(std::min<size_t>((nvox + 255) / 256, size_t(H->numSM) * 16));
+        pack_scene_kernel<<<nb, 256>>>(de, dom, da, sc->np3d, nvox, (float*)H->ext3tot.p, (float2*)H->prop3.p, (int*)H->flag.p);
+        const int ncell = S.ncx * S.ncy * S.ncz;
+        majorant_kernel<<<(ncell + 127) / 128, 128>>>((const float*)H->ext3tot.p, sc->nx, sc->ny, nz3, svx, svy, svz, S.ncx, S.ncy, S.ncz, (float*)H->maj.p);
+        const int ncol = sc->nx * sc->ny;
+        tau_up_kernel<<<(ncol + 127) / 128, 128>>>((const float*)H->ext3tot.p, S.zgrd, iz0, sc->nx, sc->ny, nz3, (float*)H->tu3.p);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        st_e.release(); st_o.release(); st_a.release();
+        int bad = 0;
+        CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) return fail(H, B200RT_ERR_ARG, "3-D field out of range (need ext >= 0, 0 <= omg <= 1, finite apf)");
+        S.ext3tot = (const float*)H->ext3tot.p; S.prop3 = (const float2*)H->prop3.p; S.ext3 = (const float*)H->ext3.p;
+        S.maj = (const float*)H->maj.p; S.tu3 = (const float*)H->tu3.p;
+    }
+
+    // ------------------------------------------------ phase tables (built in fp64 on the host, stored fp32)
+    S.pt.npf = 0; S.pt.nang = 0;
+    if (sc->npf > 0) {
+        if (sc->nang < 2) return fail(H, B200RT_ERR_ARG, "phase table needs >= 2 angles");
+        std::vector<double> ang, pha;
+        if ((rc = fetch_host(H, sc->ang, size_t(sc->nang), ang))) return rc;
+        if ((rc = fetch_host(H, sc->pha, size_t(sc->npf) * sc->nang, pha))) return rc;
+        const int na = sc->nang;
+        std::vector<float> fmu(na), fp(size_t(sc->npf) * na), fc(size_t(sc->npf) * na);
+        std::vector<double> mu(na);
+        for (int j = 0; j < na; ++j) {
+            if (j > 0 && !(ang[j] > ang[j - 1])) return fail(H, B200RT_ERR_ARG, "phase-function angles must increase");
+            mu[j] = std::cos(ang[j] * M_PI / 180.0);
+            if (j == 0 && std::fabs(ang[j]) < 1e-9) mu[j] = 1.0;
+            if (j == na - 1 && std::fabs(ang[j] - 180.0) < 1e-9) mu[j] = -1.0;
+            fmu[j] = float(mu[j]);
+        }
+        for (int t = 0; t < sc->npf; ++t) {
+            const double* p = pha.data() + size_t(t) * na;
+            std::vector<double> cdf(na, 0.0);
+            double area = 0;
+            for (int j = 1; j < na; ++j) {
+                area += 0.5 * (std::max(0.0, p[j]) + std::max(0.0, p[j - 1])) * (mu[j - 1] - mu[j]);
+                cdf[j] = area;
+            }
+            if (!(area > 0)) return fail(H, B200RT_ERR_ARG, "phase function integrates to zero");
+            for (int j = 0; j < na; ++j) {
+                fp[size_t(t) * na + j] = float(std::max(0.0, p[j]) * 2.0 / area);
+                fc[size_t(t) * na + j] = float(cdf[j] / area);
+            }
+            fc[size_t(t) * na + na - 1] = 1.0f;
+        }
+        if ((rc = upload(H, H->pmu, fmu)) || (rc = upload(H, H->pp, fp)) || (rc = upload(H, H->pcdf, fc))) return rc;
+        S.pt.npf = sc->npf; S.pt.nang = na;
+        S.pt.mu = (const float*)H->pmu.p; S.pt.p = (const float*)H->pp.p; S.pt.cdf = (const float*)H->pcdf.p;
+    }
+
+    // ------------------------------------------------ surface
+    {
+        const size_t sn = size_t(sc->sfc_nx) * sc->sfc_ny;
+        std::vector<int32_t> st;
+        std::vector<float> sp;
+        if ((rc = fetch_host(H, sc->sfc_type, sn, st))) return rc;
+        if ((rc = fetch_host(H, sc->sfc_param, sn * 5, sp))) return rc;
+        for (size_t i = 0; i < sn; ++i) {
+            if (st[i] != B200RT_SFC_LAMBERT && st[i] != B200RT_SFC_DSM && st[i] != B200RT_SFC_LSRT)
+                return fail(H, B200RT_ERR_ARG, "unsupported surface type (1 Lambertian, 2 DSM, 4 LSRT)");
+            if (!std::isfinite(sp[i])) return fail(H, B200RT_ERR_ARG, "non-finite surface parameter");
+        }
+        if ((rc = upload(H, H->sfc_type, st)) || (rc = upload(H, H->sfc_param, sp))) return rc;
+        S.sfc_nx = sc->sfc_nx; S.sfc_ny = sc->sfc_ny;
+        S.sfc_type = (const int*)H->sfc_type.p; S.sfc_param = (const float*)H->sfc_param.p;
+    }
+
+    // ------------------------------------------------ source and sensors
+    S.src = dir_from_angles(sc->src_the, sc->src_phi);
+    if (!(S.src.z < 0.0f)) return fail(H, B200RT_ERR_ARG, "source must travel downward (Src_the > 90)");
+    S.mu0 = float(-std::cos(sc->src_the * M_PI / 180.0));
+    S.src_cos_half = float(std::cos(0.5 * sc->src_qmax * M_PI / 180.0));
+    H->src_flx = sc->src_flx;
+    S.nrad = sc->nrad;
+    long long off = 0;
+    for (int k = 0; k < sc->nrad; ++k) {
+        const b200rt_sensor& q = sc->sensors[k];
+        if (q.kind != 2) return fail(H, B200RT_ERR_ARG, "only Rad_mrkind = 2 (satellite) sensors are implemented");
+        if (q.nxr < 1 || q.nyr < 1) return fail(H, B200RT_ERR_ARG, "sensor pixel grid must be >= 1 x 1");
+        const float3 view = dir_from_angles(q.the, q.phi);
+        DevSensor& se = S.sens[k];
+        se.s = make_float3(view.x == 0.f ? 0.f : -view.x, view.y == 0.f ? 0.f : -view.y, -view.z);
+        if (std::fabs(se.s.z) < 1e-3f) return fail(H, B200RT_ERR_ARG, "horizontal viewing direction is not supported");
+        se.inv_sz = 1.0f / std::fabs(se.s.z);
+        se.zt = float(std::min(zg[nz], std::max(zg[0], q.zloc)));
+        se.zref = float(q.zref);
+        se.lt = 0;
+        for (int i = 0; i < nz; ++i) if (se.zt >= fz[i]) se.lt = i;
+        se.nxr = q.nxr; se.nyr = q.nyr;
+        se.vertical_up = (se.s.x == 0.f && se.s.y == 0.f && se.s.z > 0.f) ? 1 : 0;
+        se.fast_ok = (nz3 == 0 || se.zt >= fz[iz0 + nz3]) ? 1 : 0;
+        se.off = off;
+        off += (long long)q.nxr * q.nyr;
+    }
+    S.rad_slab = off;
+
+    // ------------------------------------------------ tallies
+    const size_t nxy = size_t(sc->nx) * sc->ny;
+    H->nflux = (opt->target & B200RT_TARGET_FLUX) ? size_t(opt->nslab) * 3 * (nz + 1) * nxy : 0;
+    H->nrad = ((opt->target & B200RT_TARGET_RADIANCE) && sc->nrad > 0) ? size_t(opt->nslab) * size_t(off) : 0;
+    H->nheat = (opt->target & B200RT_TARGET_HEATING) ? size_t(opt->nslab) * nz * nxy : 0;
+    if ((rc = dev_alloc(H, H->flux, H->nflux * 8)) || (rc = dev_alloc(H, H->rad, H->nrad * 8)) || (rc = dev_alloc(H, H->heat, H->nheat * 8)) ||
+        (rc = dev_alloc(H, H->counter, 16)) || (rc = dev_alloc(H, H->stats, sizeof(DevStats))) || (rc = dev_alloc(H, H->flag, 16)))
+        return rc;
+    CK(cudaMemset(H->flux.p, 0, std::max<size_t>(16, H->nflux * 8)));
+    CK(cudaMemset(H->rad.p, 0, std::max<size_t>(16, H->nrad * 8)));
+    CK(cudaMemset(H->heat.p, 0, std::max<size_t>(16, H->nheat * 8)));
+    S.flux = (double*)H->flux.p; S.rad = (double*)H->rad.p; S.heat = (double*)H->heat.p;
+    S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
+
+    if (H->smem_bytes > 48 * 1024)
+        CK(cudaFuncSetAttribute(transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->smem_bytes)));
+    H->opt = *opt;
+    H->have_scene = true;
+    H->ran = false;
+    return B200RT_OK;
+}
+
+int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, void* cuda_stream) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!H->have_scene) return fail(H, B200RT_ERR_STATE, "b200rt_run called before b200rt_upload_scene");
+    if (!jobs || njob < 1) return fail(H, B200RT_ERR_ARG, "no jobs");
+    CK(cudaSetDevice(H->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DevScene& S = H->S;
+    const int nz = S.nz;
+    std::vector<DevJob> dj(njob);
+    std::vector<float> jabs(size_t(njob) * nz, 0.f), jcabs(size_t(njob) * (nz + 1), 0.f);
+    std::vector<double> jfs(size_t(njob) * (nz + 1), 1.0);
+    unsigned long long acc = 0;
+    for (int j = 0; j < njob; ++j) {
+        const b200rt_job& q = jobs[j];
+        if (q.nphot < 0) return fail(H, B200RT_ERR_ARG, "negative photon count");
+        if (q.slab < 0 || q.slab >= H->opt.nslab) return fail(H, B200RT_ERR_ARG, "job slab out of range");
+        DevJob& d = dj[j];
+        const long long world = S.shard_world, rank = S.shard_rank;
+        const long long cnt = q.nphot > rank ? (q.nphot - rank + world - 1) / world : 0;
+        d.first = acc; d.count = (unsigned long long)cnt; acc += d.count;
+        d.seed = q.seed;
+        d.norm = q.nphot > 0 ? double(S.mu0) * H->src_flx / double(q.nphot) : 0.0;
+        d.rad_scale = q.rad_scale;
+        d.slab = q.slab;
+        d.has_abs = 0; d.has_fscale = 0;
+        if (q.abs1d) {
+            double c = 0;
+            for (int i = 0; i < nz; ++i) {
+                const double a = q.abs1d[i];
+                if (!(a >= 0) || !std::isfinite(a)) return fail(H, B200RT_ERR_ARG, "Atm_abs1d must be finite and >= 0");
+                if (a > 0) d.has_abs = 1;
+                jabs[size_t(j) * nz + i] = float(a);
+                jcabs[size_t(j) * (nz + 1) + i] = float(c);
+                c += a * (double(H->h_zgrd[i + 1]) - double(H->h_zgrd[i]));
+            }
+            jcabs[size_t(j) * (nz + 1) + nz] = float(c);
+        }
+        if (q.flx_scale) {
+            d.has_fscale = 1;
+            for (int i = 0; i <= nz; ++i) jfs[size_t(j) * (nz + 1) + i] = q.flx_scale[i];
+        }
+    }
+    int rc;
+    if ((rc = upload(H, H->jobs, dj)) || (rc = upload(H, H->job_abs, jabs)) || (rc = upload(H, H->job_cabs, jcabs)) ||
+        (rc = upload(H, H->job_fscale, jfs)))
+        return rc;
+    S.njob = njob; S.jobs = (const DevJob*)H->jobs.p; S.job_abs = (const float*)H->job_abs.p;
+    S.job_cabs = (const float*)H->job_cabs.p; S.job_fscale = (const double*)H->job_fscale.p;
+    S.nphot_local = acc;
+
+    if (!accumulate) {
+        if (H->nflux) CK(cudaMemsetAsync(H->flux.p, 0, H->nflux * 8, st));
+        if (H->nrad) CK(cudaMemsetAsync(H->rad.p, 0, H->nrad * 8, st));
+        if (H->nheat) CK(cudaMemsetAsync(H->heat.p, 0, H->nheat * 8, st));
+    }
+    CK(cudaMemsetAsync(H->counter.p, 0, 16, st));
+    CK(cudaMemsetAsync(H->stats.p, 0, sizeof(DevStats), st));
+
+    int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : 256;
+    tpb = std::min(256, std::max(32, (tpb / 32) * 32));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel, tpb, H->smem_bytes));
+    if (bps < 1) return fail(H, B200RT_ERR_CUDA, "transport kernel does not fit on an SM");
+    if (H->opt.blocks_per_sm > 0) bps = std::min(bps, H->opt.blocks_per_sm);
+    unsigned long long want = (acc + tpb - 1) / tpb;
+    int grid = int(std::min<unsigned long long>((unsigned long long)H->numSM * bps, std::max<unsigned long long>(1, want)));
+    CK(cudaEventRecord(H->ev0, st));
+    transport_kernel<<<grid, tpb, H->smem_bytes, st>>>(S);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(H->ev1, st));
+    H->last_stream = st;
+    H->ran = true;
+    H->launches = 1;
+    return B200RT_OK;
+}
+
+int b200rt_sync(void* handle) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!H->ran) return fail(H, B200RT_ERR_STATE, "nothing has been run");
+    CK(cudaSetDevice(H->device));
+    cudaStream_t st = H->last_stream;
+    CK(cudaMemsetAsync(H->flag.p, 0, 16, st));
+    const int nb = H->numSM * 4;
+    if (H->nflux) check_finite_kernel<<<nb, 256, 0, st>>>((const double*)H->flux.p, H->nflux, (int*)H->flag.p);
+    if (H->nrad) check_finite_kernel<<<nb, 256, 0, st>>>((const double*)H->rad.p, H->nrad, (int*)H->flag.p);
+    if (H->nheat) check_finite_kernel<<<nb, 256, 0, st>>>((const double*)H->heat.p, H->nheat, (int*)H->flag.p);
+    H->launches = 1 + (H->nflux ? 1 : 0) + (H->nrad ? 1 : 0) + (H->nheat ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    int bad = 0;
+    CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    DevStats ds;
+    CK(cudaMemcpy(&ds, H->stats.p, sizeof(ds), cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, H->ev0, H->ev1));
+    b200rt_stats& o = H->stats_host;
+    std::memset(&o, 0, sizeof(o));
+    o.photons = ds.photons; o.n_cell = ds.n_cell; o.n_tent = ds.n_tent; o.n_coll = ds.n_coll; o.n_sfc = ds.n_sfc;
+    o.n_le = ds.n_le; o.n_le_visit = ds.n_le_visit; o.n_tally = ds.n_tally; o.n_roulette_kill = ds.n_kill;
+    o.w_toa_up = ds.w_toa; o.w_sfc_abs = ds.w_sfc; o.w_atm_abs = ds.w_atm; o.w_roulette = ds.w_rr;
+    o.elapsed_ms = ms;
+    o.bytes_alg = 4.0 * double(ds.n_cell) + 4.0 * double(ds.n_tent) + 8.0 * double(ds.n_coll) + 4.0 * double(ds.n_le_visit) +
+                  8.0 * double(ds.n_tally) + 2.0 * 8.0 * double(H->nflux + H->nrad + H->nheat);
+    o.launches = H->launches;
+    if (bad) return fail(H, B200RT_ERR_NUMERIC, "NaN/Inf found in tallies");
+    return B200RT_OK;
+}
+
+static int read_any(Handle* H, const DevBuf& b, size_t n, double* dst, int64_t count, const char* what) {
+    if (!H->ran) return fail(H, B200RT_ERR_STATE, "nothing has been run");
+    if (n == 0) return fail(H, B200RT_ERR_STATE, std::string(what) + " was not part of the target");
+    if (!dst || count < 0 || size_t(count) < n) return fail(H, B200RT_ERR_ARG, std::string("destination too small for ") + what);
+    CK(cudaSetDevice(H->device));
+    CK(cudaStreamSynchronize(H->last_stream));
+    CK(cudaMemcpy(dst, b.p, n * 8, cudaMemcpyDefault));
+    return B200RT_OK;
+}
+
+int b200rt_read_flux(void* handle, double* dst, int64_t count) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    return read_any(H, H->flux, H->nflux, dst, count, "flux");
+}
+int b200rt_read_rad(void* handle, double* dst, int64_t count) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    return read_any(H, H->rad, H->nrad, dst, count, "radiance");
+}
+int b200rt_read_heat(void* handle, double* dst, int64_t count) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    return read_any(H, H->heat, H->nheat, dst, count, "heating");
+}
+
+int b200rt_tally_ptrs(void* handle, double** flux, int64_t* nflux, double** rad, int64_t* nrad, double** heat, int64_t* nheat) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!H->have_scene) return fail(H, B200RT_ERR_STATE, "no scene");
+    if (flux) *flux = H->nflux ? (double*)H->flux.p : nullptr;
+    if (nflux) *nflux = int64_t(H->nflux);
+    if (rad) *rad = H->nrad ? (double*)H->rad.p : nullptr;
+    if (nrad) *nrad = int64_t(H->nrad);
+    if (heat) *heat = H->nheat ? (double*)H->heat.p : nullptr;
+    if (nheat) *nheat = int64_t(H->nheat);
+    return B200RT_OK;
+}
+
+int b200rt_stats_get(void* handle, b200rt_stats* out) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H || !out) return B200RT_ERR_ARG;
+    *out = H->stats_host;
+    return B200RT_OK;
+}
+
+int b200rt_philox_fill(void* handle, uint64_t seed, uint64_t first, uint32_t c2, uint32_t c3, uint32_t* out_host, int64_t n) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!out_host || n < 0) return fail(H, B200RT_ERR_ARG, "bad output buffer");
+    if (n == 0) return B200RT_OK;
+    CK(cudaSetDevice(H->device));
+    DevBuf tmp;
+    int rc = dev_alloc(H, tmp, size_t(n) * 16);
+    if (rc) return rc;
+    philox_fill_kernel<<<unsigned((n + 255) / 256), 256>>>(seed, first, c2, c3, (uint4*)tmp.p, n);
+    cudaError_t e = cudaMemcpy(out_host, tmp.p, size_t(n) * 16, cudaMemcpyDefault);
+    tmp.release();
+    if (e != cudaSuccess) return fail(H, B200RT_ERR_CUDA, cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+static int map_kernel_io(Handle* H, const double* in, size_t nin, double* out, size_t nout, DevBuf& din, DevBuf& dout) {
+    int rc;
+    if ((rc = dev_alloc(H, din, nin * 8)) || (rc = dev_alloc(H, dout, nout * 8))) return rc;
+    CK(cudaMemcpy(din.p, in, nin * 8, cudaMemcpyDefault));
+    (void)out;
+    return 0;
+}
+
+int b200rt_phase_eval(void* handle, double apf, const double* mu, double* p_out, int64_t n) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!H->have_scene) return fail(H, B200RT_ERR_STATE, "no scene");
+    if (n <= 0) return B200RT_OK;
+    CK(cudaSetDevice(H->device));
+    DevBuf a, b;
+    int rc = map_kernel_io(H, mu, n, p_out, n, a, b);
+    if (rc) return rc;
+    phase_eval_kernel<<<unsigned((n + 255) / 256), 256>>>(H->S.pt, float(apf), (const double*)a.p, (double*)b.p, n);
+    cudaError_t e = cudaMemcpy(p_out, b.p, size_t(n) * 8, cudaMemcpyDefault);
+    a.release(); b.release();
+    if (e != cudaSuccess) return fail(H, B200RT_ERR_CUDA, cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+int b200rt_phase_sample(void* handle, double apf, const double* xi, double* mu_out, int64_t n) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (!H->have_scene) return fail(H, B200RT_ERR_STATE, "no scene");
+    if (n <= 0) return B200RT_OK;
+    CK(cudaSetDevice(H->device));
+    DevBuf a, b;
+    int rc = map_kernel_io(H, xi, n, mu_out, n, a, b);
+    if (rc) return rc;
+    phase_sample_kernel<<<unsigned((n + 255) / 256), 256>>>(H->S.pt, float(apf), (const double*)a.p, (double*)b.p, n);
+    cudaError_t e = cudaMemcpy(mu_out, b.p, size_t(n) * 8, cudaMemcpyDefault);
+    a.release(); b.release();
+    if (e != cudaSuccess) return fail(H, B200RT_ERR_CUDA, cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+int b200rt_brdf_eval(void* handle, int32_t type, const float* param5, const double* dir_in3, const double* dir_out3,
+                     double* f_out, int64_t n) {
+    Handle* H = static_cast<Handle*>(handle);
+    if (!H) return B200RT_ERR_ARG;
+    if (n <= 0) return B200RT_OK;
+    CK(cudaSetDevice(H->device));
+    DevBuf a, b, c, d;
+    int rc;
+    if ((rc = dev_alloc(H, a, 5 * 4)) || (rc = dev_alloc(H, b, size_t(n) * 24)) || (rc = dev_alloc(H, c, size_t(n) * 24)) ||
+        (rc = dev_alloc(H, d, size_t(n) * 8)))
+        return rc;
+    CK(cudaMemcpy(a.p, param5, 20, cudaMemcpyDefault));
+    CK(cudaMemcpy(b.p, dir_in3, size_t(n) * 24, cudaMemcpyDefault));
+    CK(cudaMemcpy(c.p, dir_out3, size_t(n) * 24, cudaMemcpyDefault));
+    brdf_eval_kernel<<<unsigned((n + 255) / 256), 256>>>(type, (const float*)a.p, (const double*)b.p, (const double*)c.p, (double*)d.p, n);
+    cudaError_t e = cudaMemcpy(f_out, d.p, size_t(n) * 8, cudaMemcpyDefault);
+    a.release(); b.release(); c.release(); d.release();
+    if (e != cudaSuccess) return fail(H, B200RT_ERR_CUDA, cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+"""
+Parity tests proper: the CUDA path (through the C-ABI) against oracle/ on the same seeded scenes.
+
+Tolerances are the ones BASELINE.json's north_star states:
+  * energy conservation R + T + A = 1 to fp64-accumulation precision,
+  * domain-mean fluxes within 0.5 % of the oracle,
+  * per-pixel radiance within 3 combined Monte Carlo standard deviations.
+Monte Carlo on two different random streams cannot agree bit for bit; the integer parts of the path (Philox,
+photon -> job mapping) are checked bit-exactly in test_gpu_bits.py.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+import scenes
+from er3t_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+FLUX_RTOL = 0.005      # north_star: domain-mean fluxes within 0.5 %
+NSIGMA = 3.0           # north_star: per-pixel radiance within 3 combined sigma
+
+
+def run_both(solver, sc, opt, jobs, jobs_gpu=None):
+    solver.upload_scene(sc, opt)
+    solver.run(jobs if jobs_gpu is None else jobs_gpu)
+    g = solver.results()
+    c = oracle.run(sc, opt, jobs)
+    return g, c
+
+
+def close(gm, cm, z, rtol=FLUX_RTOL, nsig=3.5):
+    """within the stated relative tolerance, or -- when the Monte Carlo noise of the comparison itself is larger
+    than that -- within nsig combined standard errors."""
+    return abs(gm / cm - 1.0) < rtol or abs(z) < nsig
+
+
+def check_energy(st, tol=1e-9):
+    n = st['photons']
+    bal = (st['w_toa_up'] + st['w_sfc_abs'] + st['w_atm_abs'] - st['w_roulette']) / n - 1.0
+    assert abs(bal) < tol, bal
+
+
+def zscores(g, c, nslab, shape):
+    gm, gs = scenes.mean_sem(g.reshape((nslab,) + shape))
+    cm, cs = scenes.mean_sem(c.reshape((nslab,) + shape))
+    # fp32-vs-fp64 rounding floor: deterministic tallies (e.g. TOA down-flux) have zero Monte Carlo spread
+    den = np.sqrt(gs ** 2 + cs ** 2) + 2e-6 * np.abs(cm)
+    ok = den > 0
+    z = np.zeros_like(gm)
+    z[ok] = (gm[ok] - cm[ok]) / den[ok]
+    return z, gm, cm
+
+
+def assert_pixels(z, nslab):
+    """|z| <= 3 sigma per pixel, allowing the tail mass a Student-t with nslab-1 dof gives on many pixels."""
+    frac = np.mean(np.abs(z) > NSIGMA)
+    assert frac <= 0.03, frac
+    assert np.max(np.abs(z)) < 6.5, np.max(np.abs(z))
+    rms = np.sqrt(np.mean(z ** 2))
+    assert 0.5 < rms < 1.6, rms
+
+
+@pytest.mark.parametrize('absorb', [False, True])
+def test_plane_parallel_flux_and_radiance(solver, absorb):
+    sc, absg = scenes.plane_parallel(absorb=absorb)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=nslab, wmin=0.0)
+    jobs, keep = scenes.multi_seed_jobs(250000, nslab, abs1d=absg)
+    jobs_gpu, keep2 = scenes.multi_seed_jobs(2000000, nslab, abs1d=absg)
+    g, c = run_both(solver, sc, opt, jobs, jobs_gpu)
+    check_energy(g['stats'])
+    check_energy(c['stats'])
+    nlev = sc.struct.nz + 1
+    z, gm, cm = zscores(g['flux'], c['flux'], nslab, (3, nlev, 1, 1))
+    # domain-mean flux at every level, all three components
+    big = cm > 1e-3
+    assert np.all(np.abs(gm[big] / cm[big] - 1.0) < FLUX_RTOL), np.max(np.abs(gm[big] / cm[big] - 1.0))
+    assert np.max(np.abs(z)) < 5.0
+    zr, grm, crm = zscores(g['rad'], c['rad'], nslab, (1,))
+    assert abs(zr[0]) < 4.0
+    assert close(grm[0], crm[0], zr[0]), (grm[0], crm[0], zr[0])
+
+
+def test_plane_parallel_roulette_unbiased(solver):
+    sc, absg = scenes.plane_parallel(omega=0.9, albedo=0.5)
+    nslab = 8
+    o0 = abi.make_options(target=abi.TARGET_FLUX, nslab=nslab, wmin=0.0)
+    o1 = abi.make_options(target=abi.TARGET_FLUX, nslab=nslab, wmin=0.2, wfac=1.0)
+    jobs, keep = scenes.multi_seed_jobs(100000, nslab)
+    solver.upload_scene(sc, o0); solver.run(jobs); a = solver.results()
+    solver.upload_scene(sc, o1); solver.run(jobs); b = solver.results()
+    check_energy(a['stats']); check_energy(b['stats'])
+    assert b['stats']['n_roulette_kill'] > 0
+    z, am, bm = zscores(a['flux'], b['flux'], nslab, (3, sc.struct.nz + 1, 1, 1))
+    assert np.max(np.abs(z)) < 5.0
+    assert abs(bm[2, -1, 0, 0] / am[2, -1, 0, 0] - 1.0) < FLUX_RTOL
+
+
+@pytest.mark.parametrize('sfc', ['lambert', 'lambert2d', 'lsrt', 'dsm'])
+def test_3d_radiance_nadir(solver, sfc):
+    sc = scenes.scene_3d(sfc=sfc)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE | abi.TARGET_FLUX, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(200000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    nx, ny = sc.struct.nx, sc.struct.ny
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (ny, nx))
+    assert_pixels(z, nslab)
+    assert abs(gm.mean() / cm.mean() - 1.0) < FLUX_RTOL
+    # domain-mean fluxes at TOA and surface
+    gf = g['flux'].reshape(nslab, 3, -1, ny, nx).mean(axis=(0, 3, 4))
+    cf = c['flux'].reshape(nslab, 3, -1, ny, nx).mean(axis=(0, 3, 4))
+    for var, lev in ((2, -1), (1, 0), (0, 0), (2, 0)):
+        assert abs(gf[var, lev] / cf[var, lev] - 1.0) < FLUX_RTOL, (var, lev, gf[var, lev], cf[var, lev])
+
+
+@pytest.mark.parametrize('sv', [(1, 1, 1), (4, 4, 2), (16, 12, 4)])
+def test_3d_supervoxel_sizes_agree_with_exact_traversal(solver, sv):
+    """Null-collision tracking on any majorant grid must reproduce the oracle's exact traversal."""
+    sc = scenes.scene_3d(sensors=[dict(the=180.0, phi=270.0, nxr=16, nyr=12)])
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2, sv=sv)
+    jobs, keep = scenes.multi_seed_jobs(200000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    assert abs(gm.mean() / cm.mean() - 1.0) < FLUX_RTOL
+
+
+def test_3d_oblique_multi_sensor(solver):
+    sens = [dict(the=180.0, phi=270.0, nxr=16, nyr=12),
+            dict(the=180.0 - 35.0, phi=30.0, nxr=16, nyr=12),
+            dict(the=180.0 - 60.0, phi=250.0, nxr=8, nyr=6),
+            dict(the=180.0 - 20.0, phi=100.0, nxr=16, nyr=12, zloc=900.0)]    # inside the cloud layer block
+    sc = scenes.scene_3d(sensors=sens, sfc='lsrt')
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(150000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    per = [16 * 12, 16 * 12, 8 * 6, 16 * 12]
+    gr = g['rad'].reshape(nslab, -1); cr = c['rad'].reshape(nslab, -1)
+    off = 0
+    for n in per:
+        z, gm, cm = zscores(gr[:, off:off + n].copy(), cr[:, off:off + n].copy(), nslab, (n,))
+        assert_pixels(z, nslab)
+        assert abs(gm.mean() / cm.mean() - 1.0) < 2 * FLUX_RTOL
+        off += n
+
+
+@pytest.mark.parametrize('solver_mode', [abi.SOLVER_IPA, abi.SOLVER_PARTIAL_3D])
+def test_3d_ipa_and_partial(solver, solver_mode):
+    sc = scenes.scene_3d()
+    nslab = 8
+    opt = abi.make_options(solver=solver_mode, target=abi.TARGET_RADIANCE | abi.TARGET_FLUX, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(150000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    assert abs(gm.mean() / cm.mean() - 1.0) < FLUX_RTOL
+
+
+def test_3d_two_components_table_phase_heating(solver):
+    sc = scenes.scene_3d(two_comp=True, apf_mode='table')
+    nslab = 8
+    absg = np.full(sc.struct.nz, 2.0e-5)
+    opt = abi.make_options(target=abi.TARGET_RADIANCE | abi.TARGET_FLUX | abi.TARGET_HEATING, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(150000, nslab, abs1d=absg)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    assert abs(gm.mean() / cm.mean() - 1.0) < FLUX_RTOL
+    gh = g['heat'].reshape(nslab, sc.struct.nz, -1).mean(axis=(0, 2))
+    ch = c['heat'].reshape(nslab, sc.struct.nz, -1).mean(axis=(0, 2))
+    assert np.all(np.abs(gh / ch - 1.0) < 0.01), np.max(np.abs(gh / ch - 1.0))
+    # absorbed energy in the heating tally equals the atmospheric absorption counter
+    n = g['stats']['photons'] / nslab
+    mu0 = np.cos(np.deg2rad(40.0))
+    assert abs(g['heat'].reshape(nslab, -1).sum(axis=1).mean() / (12 * 16) / mu0 - g['stats']['w_atm_abs'] / nslab / n) < 1e-6
+
+
+def test_cyclic_shift_invariance(solver):
+    """3-D result is invariant under a cyclic shift of the field (SURVEY.md 8c identity)."""
+    sc = scenes.scene_3d(sfc='lambert')
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(200000, nslab)
+    solver.upload_scene(sc, opt); solver.run(jobs); a = solver.read_rad().reshape(nslab, 12, 16)
+    ext = np.transpose(sc.ext3d, (3, 2, 1, 0)); omg = np.transpose(sc.omg3d, (3, 2, 1, 0)); apf = np.transpose(sc.apf3d, (3, 2, 1, 0))
+    sh = (5, 3)
+    sc2 = abi.HostScene(sc.zgrd, sc.ext1d, sc.omg1d, sc.apf1d, nx=16, ny=12, dx=100.0, dy=100.0, iz3l=sc.struct.iz3l,
+                        ext3d=np.roll(ext, sh, axis=(0, 1)), omg3d=np.roll(omg, sh, axis=(0, 1)), apf3d=np.roll(apf, sh, axis=(0, 1)),
+                        sfc_type=1, sfc_param=(0.1, 0, 0, 0, 0), src_the=sc.struct.src_the, src_phi=sc.struct.src_phi,
+                        sensors=[dict(the=180.0, phi=270.0, nxr=16, nyr=12)])
+    jobs2, keep2 = scenes.multi_seed_jobs(200000, nslab, seed0=555)
+    solver.upload_scene(sc2, opt); solver.run(jobs2); b = solver.read_rad().reshape(nslab, 12, 16)
+    b = np.roll(b, (-sh[1], -sh[0]), axis=(1, 2))
+    z, am, bm = zscores(a, b, nslab, (12, 16))
+    assert_pixels(z, nslab)
