@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
                     const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
                     const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                     tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                              (double(p.w) - double(wn)) * J.norm * double(nxy));
+                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
                     ++n_tally;
                 }
                 p.w = wn;
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
                         const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
                         const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                         tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                                  (double(p.w) - double(wn)) * J.norm * double(nxy));
+                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
                         ++n_tally;
                     }
                 }
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
                     const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
                     const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                     tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                              (double(p.w) - double(wn)) * J.norm * double(nxy));
+                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
                     ++n_tally;
                 }
                 p.w = wn;

@@ -112,7 +112,8 @@ typedef struct b200rt_job {
     int32_t  slab;                /* output slab the job accumulates into (run index, or job index for raw output) */
     int32_t  _pad;
     const double* abs1d;          /* [nz] gas absorption coefficient 1/m (Atm_abs1d(1:,1)), NULL = 0; host pointer */
-    const double* flx_scale;      /* [nz+1] per-level factor (mca_out.py:324-327), NULL = 1; host pointer          */
+    const double* flx_scale;      /* [nz+1] per-level factor (mca_out.py:324-327), NULL = 1; host pointer;
+                                     entry iz also scales the heating tally of layer iz                             */
     double   rad_scale;           /* factor for radiance (mca_out.py:449-452, iz = 0)          */
 } b200rt_job;
 

@@ -504,7 +504,7 @@ void trace_photon(const Scene& S, const JobCtx& J, const Tally& T, Philox& R, Co
                 if (T.heat) {
                     int hx = p.ix, hy = p.iy;
                     if (!is3 && !p.frozen) { hx = clampi(int(std::floor(p.x / S.dx)), 0, S.nx - 1); hy = clampi(int(std::floor(p.y / S.dy)), 0, S.ny - 1); }
-                    T.add(&T.heat[(size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx], dep * J.norm * double(nxy));
+                    T.add(&T.heat[(size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx], dep * J.norm * double(nxy) * (J.fscale ? J.fscale[iz] : 1.0));
                 }
                 p.w = wn;
             }
@@ -574,7 +574,7 @@ void trace_photon(const Scene& S, const JobCtx& J, const Tally& T, Philox& R, Co
             if (T.heat && p.w > wn) {
                 int hx = p.ix, hy = p.iy;
                 if (!is3 && !p.frozen) { hx = clampi(int(std::floor(p.x / S.dx)), 0, S.nx - 1); hy = clampi(int(std::floor(p.y / S.dy)), 0, S.ny - 1); }
-                T.add(&T.heat[(size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx], (p.w - wn) * J.norm * double(nxy));
+                T.add(&T.heat[(size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx], (p.w - wn) * J.norm * double(nxy) * (J.fscale ? J.fscale[iz] : 1.0));
             }
             p.w = wn;
             p.order++; p.direct = false;
