@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the photon-transport path: photons/s on the 3-D LES cloud radiance config
+(BASELINE.json configs[1]: 480 x 480 x 100 voxels at 100 m, nadir radiance at 650 nm, 1e8 photons per set, 3 runs,
+16 g weighted -- projects/05_cnn-les_rad-sim shape, examples/00_er3t_mca.py::example_05).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on the host cores
+
+One "step" = one complete `mcarats_ng` job set (Nrun x Ng jobs = 3 x 1e8 photons) over the synthetic scene.
+`value`  : photons/s with the scene already resident in HBM (b200rt_run only; CUDA events on the launching stream).
+`e2e`    : photons/s through the public API (mcarats_ng + mca_out_ng) with HOST numpy inputs: scene packing, H2D,
+           transport, D2H and the run statistics are all inside the timed region.
+Inputs are larger than L2 (3-D fields 370 MB in HBM vs 126 MB L2), so no explicit L2 flush between iterations.
+Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import datetime
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260101
+
+
+def build_workload(nx=480, ny=480, nz3=100, photons=1e8, nrun=3):
+    """BASELINE.json configs[1] as synthetic input (SURVEY.md 8d 'C2'): returns kwargs for mcarats_ng + abs object."""
+    from er3t_b200.pre import atm_atmmod, abs_16g, pha_mie_wc, cld_gen_les
+    from er3t_b200.rtm.mca import mca_atm_1d, mca_atm_3d, mca_sca
+    dz = 4.0 / nz3                                               # 3-D block spans 0.5 .. 4.5 km
+    levels = np.concatenate(([0.0], 0.5 + dz * np.arange(nz3 + 1), np.arange(5.0, 20.1, 1.0)))
+    atm0 = atm_atmmod(levels=levels)
+    abs0 = abs_16g(wavelength=650.0, atm_obj=atm0)
+    cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=0.1, dy=0.1, altitude=0.5 + dz * (np.arange(nz3) + 0.5), seed=2, atm_obj=atm0)
+    pha0 = pha_mie_wc(wavelength=650.0)
+    sca = mca_sca(pha_obj=pha0)
+    atm3d0 = mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True)
+    atm1d0 = mca_atm_1d(atm_obj=atm0, abs_obj=abs0)
+    kw = dict(date=datetime.datetime(2017, 8, 13), atm_1ds=[atm1d0], atm_3ds=[atm3d0], Ng=abs0.Ng, target='radiance',
+              surface_albedo=0.03, sca=sca, solar_zenith_angle=28.9, solar_azimuth_angle=296.83,
+              sensor_zenith_angle=0.0, sensor_azimuth_angle=0.0, sensor_altitude=705000.0, fdir='tmp-data/bench',
+              Nrun=nrun, photons=photons, weights=abs0.coef['weight']['data'], solver='3D', quiet=True, seed=SEED,
+              iz3l_fix=True)
+    return kw, abs0
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smmax, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            w = [x.strip() for x in line.split(',')]
+            if len(w) < 9:
+                continue
+            try:
+                sm.append(float(w[1])); smmax.append(float(w[2])); power.append(float(w[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), w[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # median over samples taken under load (power above the idle floor)
+            load = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(smmax)), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(max(power)))
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the transport kernel from the committed ncu --set full capture (or None)."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)).get('transport_kernel_dram_bytes_per_launch')
+        except Exception:
+            return None
+    return None
+
+
+def cpu_oracle_rate(kw, abs0, seconds=15.0, nthreads=0):
+    """Bounded sample of the same workload on the host cores with the oracle port; returns (photons/s, photons, cores)."""
+    import oracle
+    from er3t_b200.rtm.mca import mcarats_ng
+    cores = nthreads if nthreads > 0 else (os.cpu_count() or 1)
+    rate = None
+    nphot = 40000
+    total_t = 0.0
+    while True:
+        k = dict(kw)
+        k.update(photons=nphot, Nrun=1, dry_run=True)
+        m = mcarats_ng(**k)
+        from er3t_b200 import abi
+        jobs, keep = abi.make_jobs(**m.jobs_args)
+        t0 = time.time()
+        oracle.run(m.scene, m.options, jobs, nthreads=nthreads)
+        dt = time.time() - t0
+        total_t += dt
+        rate = nphot / dt
+        if total_t >= 0.6 * seconds or nphot >= 5e7:
+            return rate, nphot, cores
+        nphot = int(max(nphot * 2, min(5e7, rate * (seconds - total_t) * 0.8)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--photons', type=float, default=1e8, help='photons per set (BASELINE: 1e8)')
+    ap.add_argument('--nx', type=int, default=480)
+    ap.add_argument('--nz3', type=int, default=100)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sv', type=str, default='0,0,0')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    workload = 'C2 3D LES-like cloud %dx%dx%d voxels @100 m (3-D block 0.5-4.5 km), nadir radiance 650 nm, %g photons/set x 3 runs x 16 g' % (
+        args.nx, args.nx, args.nz3, args.photons)
+    config = {'workload': workload, 'nx': args.nx, 'ny': args.nx, 'nz3': args.nz3, 'photons_per_set': args.photons, 'Nrun': 3, 'Ng': 16,
+              'l2': 'inputs larger than L2 (no flush)', 'parallelism': 'photons sharded over %d GPU(s), one NCCL all-reduce of tallies' % world}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        kw, abs0 = build_workload(args.nx, args.nx, args.nz3, args.photons)
+        import oracle
+        from er3t_b200 import abi
+        from er3t_b200.rtm.mca import mcarats_ng
+        cores = os.cpu_count() or 1
+        # size the per-step sample from a probe so that the whole run ends within a few minutes
+        probe, _, _ = cpu_oracle_rate(kw, abs0, seconds=6.0)
+        nstep = max(1, args.steps + args.warmup)
+        sample = int(max(2e4, min(args.photons, probe * 100.0 / nstep)))
+        k = dict(kw); k.update(photons=sample, Nrun=1, dry_run=True)
+        m = mcarats_ng(**k)
+        jobs, keep = abi.make_jobs(**m.jobs_args)
+        for _ in range(args.warmup):
+            oracle.run(m.scene, m.options, jobs)
+        t0 = time.time()
+        for _ in range(args.steps):
+            oracle.run(m.scene, m.options, jobs)
+        dt = time.time() - t0
+        val = sample * args.steps / dt
+        line = {'impl': 'reference', 'metric': 'photons/s', 'value': val, 'unit': 'photons/s', 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': val, 'unit': 'photons/s', 'cores': cores, 'kind': 'port',
+                                 'sample': '%d photons per step of the same scene (1 run x 16 g), oracle/oracle_mc.cpp with OpenMP; MCARaTS itself cannot be built offline' % sample},
+                'e2e': {'value': val, 'unit': 'photons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ this repo (CUDA)
+    import torch
+    from er3t_b200 import abi, dist as edist
+    from er3t_b200.solver import Solver
+    from er3t_b200.rtm.mca import mcarats_ng, mca_out_ng
+
+    if not torch.cuda.is_available():
+        raise OSError('Error [bench]: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm).')
+    rank, world, local = edist.init_from_env()
+    torch.cuda.set_device(local)
+    # weak scaling: every GPU traces the full BASELINE photon count, the job set grows with the number of GPUs
+    kw, abs0 = build_workload(args.nx, args.nx, args.nz3, args.photons * world)
+    kw['device'] = local
+    kw['supervoxel'] = tuple(int(v) for v in args.sv.split(','))
+    kw['shard'] = (rank, world)
+
+    sol = Solver(device=local)
+    prep = mcarats_ng(**dict(kw, dry_run=True))
+    jobs, keep = abi.make_jobs(**prep.jobs_args)
+    sol.upload_scene(prep.scene, prep.options)
+    photons_step = int(np.sum(prep.jobs_args['nphot']))          # whole job set, all ranks
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        sol.run(jobs, sync=False)
+        if world > 1:
+            return edist.allreduce_results(sol, to_host=False)
+        sol.sync()
+        return None
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, bytes_alg, launches = [], [], 0
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+        st = sol.stats() if world == 1 else None
+        if st is not None:
+            kern_ms.append(st['elapsed_ms']); bytes_alg.append(st['bytes_alg']); launches += int(st['launches'])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        sol.sync()
+        st = sol.stats()
+        kern_ms.append(st['elapsed_ms']); bytes_alg.append(st['bytes_alg']); launches = int(st['launches']) * args.steps
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler is not None else None
+    value = photons_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API (host inputs, H2D and D2H inside the timed region)
+    e2e = None
+    esteps = max(1, args.e2e_steps)
+    h2d = d2h = 0
+    def step_e2e():
+        m = mcarats_ng(**dict(kw, solver_obj=sol, reduce=(lambda s: edist.allreduce_results(s)) if world > 1 else None))
+        out = mca_out_ng(mca_obj=m, abs_obj=abs0, mode='mean', squeeze=True)
+        return m, out
+    step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(esteps):
+        m, out = step_e2e()
+    barrier()
+    dt = time.time() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = int(m.h2d_bytes)
+    d2h = int(8 * prep.scene.rad_size(prep.nslab))
+    e2e = {'value': photons_step * esteps / dt, 'unit': 'photons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'steps': esteps, 'ms_per_step': 1e3 * dt / esteps,
+           'api': 'er3t_b200.rtm.mca.mcarats_ng(...) + mca_out_ng(...) with host numpy inputs (pageable memory)'}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    t_kernel = float(np.mean(kern_ms)) * 1e-3
+    achieved = float(np.mean(bytes_alg)) / t_kernel / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'transport_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': ncu_traffic(), 'peak_source': peak_src, 'bytes_alg_per_launch': float(np.mean(bytes_alg)),
+                'kernel_ms_per_launch': float(np.mean(kern_ms)),
+                'bytes_alg_per_photon': float(np.mean(bytes_alg)) / (photons_step / world)}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r, n, cores = cpu_oracle_rate(kw, abs0, seconds=15.0)
+        cpu = {'value': r, 'unit': 'photons/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d photons of the same scene (1 run x 16 g) on the host cores, oracle/oracle_mc.cpp (fp64, exact traversal, OpenMP)' % n}
+    line = {'metric': 'photons/s', 'value': value, 'unit': 'photons/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 (fp64 tallies)', 'data': 'synthetic', 'config': config,
+            'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+            'photons_per_step': photons_step}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -26,6 +26,7 @@
 struct DevSensor {
     float3 s;            // direction of photon travel toward the sensor (= -viewing vector)
     float inv_sz;        // 1 / |s.z|
+    float inv_szs;       // 1 / s.z (signed)
     float zt;            // target level of the transmittance integral: clamp(zloc, z0, ztoa)
     float zref;
     int lt;              // layer that contains zt (nz-1 when zt == ztoa)
@@ -54,10 +55,13 @@ struct DevStats {
 
 struct DevScene {
     int nx, ny, nz, iz0, nz3, np1d, np3d;
-    float dx, dy, Lx, Ly, inv_dx, inv_dy;
+    float dx, dy, Lx, Ly, inv_dx, inv_dy, inv_Lx, inv_Ly;
     int svx, svy, svz, ncx, ncy, ncz;
     float Sx, Sy, inv_Sx, inv_Sy;
     int nslab_z;
+    int ngroup;               // coarse z groups of fine slabs
+    int nCx, nCy, shx, shy;   // coarse (emptiness) grid: 2^shx x 2^shy fine cells per coarse cell
+    int flight_steps;
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
     const float* e1tot;       // [nz]
@@ -68,6 +72,11 @@ struct DevScene {
     const int* slab_lay0;     // [nslab_z+1]
     const int* slab_cz;       // [nslab_z]
     const float* slab_maj1d;  // [nslab_z]
+    const int* slab_cg;       // [nslab_z]
+    const float* group_maj1d; // [ngroup]
+    const int* group_lo;      // [ngroup+1]
+    const int* group_cz;      // [ngroup]
+    const unsigned char* empty3; // [nCz][nCy][nCx] 1 = coarse cell holds no 3-D extinction
     // 3-D block in HBM
     const float* ext3tot;     // [nz3][ny][nx]
     const float2* prop3;      // [np3d][nz3][ny][nx]  (omega, apf)
@@ -134,6 +143,20 @@ __global__ void majorant_kernel(const float* __restrict__ ext3tot, int nx, int n
     maj[c] = m;
 }
 
+__global__ void empty_kernel(const float* __restrict__ maj, int ncx, int ncy, int shx, int shy, int nCx, int nCy, int nCz,
+                             const int* __restrict__ gz_lo, unsigned char* __restrict__ empty3) {
+    // gz_lo[K] .. gz_lo[K+1]: fine z indices (in the majorant grid) covered by coarse z cell K
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCx * nCy * nCz) return;
+    const int Cx = c % nCx, Cy = (c / nCx) % nCy, Cz = c / (nCx * nCy);
+    float m = 0.0f;
+    for (int kz = gz_lo[Cz]; kz < gz_lo[Cz + 1]; ++kz)
+        for (int ky = Cy << shy; ky < min(ncy, (Cy + 1) << shy); ++ky)
+            for (int kx = Cx << shx; kx < min(ncx, (Cx + 1) << shx); ++kx)
+                m = fmaxf(m, maj[(size_t(kz) * ncy + ky) * ncx + kx]);
+    empty3[c] = m > 0.0f ? 0 : 1;
+}
+
 __global__ void tau_up_kernel(const float* __restrict__ ext3tot, const float* __restrict__ zgrd, int iz0, int nx, int ny,
                               int nz3, float* __restrict__ tu3) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,26 +186,35 @@ struct Smem {
     const float* e1;      // [np1d][nz]
     const float* o1;
     const float* a1;
-    const int* lay0;      // [nslab_z+1]
-    const int* cz;        // [nslab_z]
-    const float* maj1d;   // [nslab_z]
+    const float* maj1d;   // [nslab_z]   majorant of the 1-D part of a fine z slab
+    const int* lay0;      // [nslab_z+1] first layer of each fine z slab
+    const int* cz;        // [nslab_z]   fine z index in the majorant grid, -1 for 1-D slabs
+    const int* cg;        // [nslab_z]   coarse group of each fine slab
+    const float* g_maj1d; // [ngroup]    majorant of the 1-D part of a coarse group
+    const int* g_lo;      // [ngroup+1]  first fine slab of each coarse group
+    const int* g_cz;      // [ngroup]    coarse z index in the emptiness grid, -1 for pure 1-D groups
 };
 
 struct Photon {
     float x, y, z;
     float3 d;
     float w;
-    float tau;
-    int cix, ciy;     // coarse cell (3-D slabs) -- the column itself when frozen
-    int is;           // z slab
-    int iz;           // layer
+    float tau;        // optical depth left until the next tentative collision
+    int cix, ciy;     // fine majorant cell (3-D slabs) -- the column itself when frozen
+    int is;           // fine z slab
+    int iz;           // layer of the last event / crossing
     int order;
     int job;
+    float za;         // start of the current straight leg (for path-integrated gas absorption)
+    int iza;
+    float leg;        // length of the current leg
     bool direct, frozen;
 };
 
-__device__ __forceinline__ float wrapf(float x, float L) {
-    x -= L * floorf(x / L);
+enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3 };
+
+__device__ __forceinline__ float wrapf(float x, float L, float invL) {
+    x -= L * floorf(x * invL);
     if (x >= L) x = 0.0f;
     if (x < 0.0f) x = 0.0f;
     return x;
@@ -205,7 +237,17 @@ __device__ __forceinline__ void flux_tally(const DevScene& S, const DevJob& J, c
     ++n_tally;
 }
 
-// gas-absorption optical depth of a straight segment inside one z slab
+// layer that contains z among layers [l0, l1)
+__device__ __forceinline__ int find_layer(const Smem& sm, int l0, int l1, float z) {
+    int lo = l0, hi = l1 - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (z >= sm.z[mid]) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// gas-absorption optical depth of a straight leg from (za, layer iza) to (zb, layer izb) of length `dist`
 __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int job, float za, int iza, float zb, int izb,
                                          float dist, float inv_absdz) {
     const float* ab = S.job_abs + size_t(job) * S.nz;
@@ -260,7 +302,7 @@ __device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, 
         const bool l3 = (S.nz3 > 0) && l >= S.iz0 && l < S.iz0 + S.nz3;
         if (!l3) {
             tau += base * dl;
-            if (!p.frozen) { x = wrapf(x + se.s.x * dl, S.Lx); y = wrapf(y + se.s.y * dl, S.Ly); }
+            if (!p.frozen) { x = wrapf(x + se.s.x * dl, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * dl, S.Ly, S.inv_Ly); }
             have_col = p.frozen;
         } else if (p.frozen) {
             tau += (base + __ldg(S.ext3tot + size_t(l - S.iz0) * nxy + size_t(fy) * S.nx + fx)) * dl;
@@ -299,7 +341,7 @@ __device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, 
     return tau;
 }
 
-// deposit one local-estimate contribution (f = angular density toward the sensor, 1/sr, already times weight)
+// deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
 __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevJob& J, const DevSensor& se,
                                            const Photon& p, float fw, int fx, int fy, float s3, unsigned& n_le,
                                            unsigned& n_visit, unsigned& n_tally) {
@@ -311,19 +353,27 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
         px = min(se.nxr - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(se.nxr)));
         py = min(se.nyr - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(se.nyr)));
     } else {
-        const float t = (se.zref - p.z) / se.s.z;
-        const float xr = wrapf(p.x + se.s.x * t, S.Lx), yr = wrapf(p.y + se.s.y * t, S.Ly);
-        px = min(se.nxr - 1, max(0, int(xr / S.Lx * float(se.nxr))));
-        py = min(se.nyr - 1, max(0, int(yr / S.Ly * float(se.nyr))));
+        const float t = (se.zref - p.z) * se.inv_szs;
+        const float xr = wrapf(p.x + se.s.x * t, S.Lx, S.inv_Lx), yr = wrapf(p.y + se.s.y * t, S.Ly, S.inv_Ly);
+        px = min(se.nxr - 1, max(0, int(xr * S.inv_Lx * float(se.nxr))));
+        py = min(se.nyr - 1, max(0, int(yr * S.inv_Ly * float(se.nyr))));
     }
     tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + size_t(py) * se.nxr + px,
               double(contrib) * J.norm * J.rad_scale * double(se.nxr) * double(se.nyr));
     ++n_tally;
 }
 
-__global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ DevScene S) {
+__device__ __forceinline__ float3 inv_dir(const float3 d) {
+    return make_float3(d.x != 0.0f ? 1.0f / d.x : RT_INF, d.y != 0.0f ? 1.0f / d.y : RT_INF, d.z != 0.0f ? 1.0f / d.z : RT_INF);
+}
+
+// Persistent-thread photon transport.  Every thread owns one photon at a time and regenerates it in place from a
+// global atomic counter.  The body is organised in warp-convergent PHASES to fight divergence:
+//   (1) regeneration of all dead lanes,
+//   (2) a bounded flight loop (cheap, branch-light cell crossings + null collisions on the two-level majorant grid),
+//   (3) one event phase shared by real collisions and surface hits (local estimates, new direction, roulette).
+__global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float smem_f[];
-    // ---- stage the 1-D tables into shared memory
     Smem sm;
     {
         float* q = smem_f;
@@ -334,21 +384,28 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
         float* o1 = q; q += S.np1d * S.nz;
         float* a1 = q; q += S.np1d * S.nz;
         float* maj1d = q; q += S.nslab_z;
+        float* g_maj1d = q; q += S.ngroup;
         int* lay0 = reinterpret_cast<int*>(q); q += S.nslab_z + 1;
-        int* cz = reinterpret_cast<int*>(q);
+        int* cz = reinterpret_cast<int*>(q); q += S.nslab_z;
+        int* cg = reinterpret_cast<int*>(q); q += S.nslab_z;
+        int* g_lo = reinterpret_cast<int*>(q); q += S.ngroup + 1;
+        int* g_cz = reinterpret_cast<int*>(q);
         for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
         for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
-        for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) { maj1d[i] = S.slab_maj1d[i]; cz[i] = S.slab_cz[i]; }
+        for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) { maj1d[i] = S.slab_maj1d[i]; cz[i] = S.slab_cz[i]; cg[i] = S.slab_cg[i]; }
         for (int i = threadIdx.x; i <= S.nslab_z; i += blockDim.x) lay0[i] = S.slab_lay0[i];
+        for (int i = threadIdx.x; i < S.ngroup; i += blockDim.x) { g_maj1d[i] = S.group_maj1d[i]; g_cz[i] = S.group_cz[i]; }
+        for (int i = threadIdx.x; i <= S.ngroup; i += blockDim.x) g_lo[i] = S.group_lo[i];
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
-        sm.maj1d = maj1d; sm.lay0 = lay0; sm.cz = cz;
+        sm.maj1d = maj1d; sm.lay0 = lay0; sm.cz = cz; sm.cg = cg; sm.g_maj1d = g_maj1d; sm.g_lo = g_lo; sm.g_cz = g_cz;
     }
     __syncthreads();
 
     const bool want_flux = (S.target & B200RT_TARGET_FLUX) != 0;
     const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
     const bool want_heat = (S.target & B200RT_TARGET_HEATING) != 0;
+    const bool per_level = want_flux || want_heat;       // every z crossing is a level crossing (svz = 1, no groups)
     const size_t nxy = size_t(S.nx) * S.ny;
 
     unsigned n_cell = 0, n_tent = 0, n_coll = 0, n_sfc = 0, n_le = 0, n_visit = 0, n_tally = 0, n_kill = 0, n_phot = 0;
@@ -359,12 +416,19 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
     DevJob J;
     float3 invd = make_float3(0.f, 0.f, 0.f);
     bool alive = false;
+    bool exhausted = false;
     p.job = -1;
     g.c3 = 0xB200u;
+    // collision hand-off from the flight loop to the event phase
+    float ev_s3 = 0.0f, ev_uc = 0.0f;
+    float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ev_fx = 0, ev_fy = 0;
+    size_t ev_vox = 0;
+    bool ev_in3 = false;
 
     for (;;) {
-        if (!alive) {
-            // ---- regeneration: warp-aggregated fetch of the next photon index
+        // =========================================================== (1) regeneration
+        if (!alive && !exhausted) {
             const unsigned mask = __activemask();
             const int lane = threadIdx.x & 31;
             const int leader = __ffs(mask) - 1;
@@ -372,72 +436,91 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
             if (lane == leader) base = atomicAdd(S.counter, (unsigned long long)__popc(mask));
             base = __shfl_sync(mask, base, leader);
             const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1u));
-            if (idx >= S.nphot_local) break;
-            // job look-up (jobs are few; binary search on the prefix sums)
-            int lo = 0, hi = S.njob - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
-            }
-            if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
-            const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
-            g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
-            g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
-            const float4 u = rng4(g);
-            const float4 v = rng4(g);
-            p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
-            if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
-            else p.d = S.src;
-            p.w = 1.0f; p.order = 0; p.direct = true;
-            p.is = S.nslab_z - 1; p.iz = S.nz - 1;
-            p.frozen = (S.solver == B200RT_SOLVER_IPA);
-            p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
-            p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
-            if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
-            p.tau = -__logf(v.x);
-            invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
-            invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
-            invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
-            alive = true;
-            ++n_phot;
-            if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
-        }
-
-        // ---- one event step inside the current cell
-        const int is = p.is;
-        const int l0 = sm.lay0[is], l1 = sm.lay0[is + 1];
-        const float zlo = sm.z[l0], zhi = sm.z[l1];
-        const int cz = sm.cz[is];
-        const bool in3 = cz >= 0;
-        float M = sm.maj1d[is];
-        float tz = RT_INF, tx = RT_INF, ty = RT_INF;
-        if (p.d.z > 0.0f) tz = (zhi - p.z) * invd.z; else if (p.d.z < 0.0f) tz = (zlo - p.z) * invd.z;
-        if (in3) {
-            M += __ldg(S.maj + (size_t(cz) * S.ncy + p.ciy) * S.ncx + p.cix);
-            ++n_cell;
-            if (!p.frozen) {
-                if (p.d.x > 0.0f) tx = (fminf(float(p.cix + 1) * S.Sx, S.Lx) - p.x) * invd.x;
-                else if (p.d.x < 0.0f) tx = (float(p.cix) * S.Sx - p.x) * invd.x;
-                if (p.d.y > 0.0f) ty = (fminf(float(p.ciy + 1) * S.Sy, S.Ly) - p.y) * invd.y;
-                else if (p.d.y < 0.0f) ty = (float(p.ciy) * S.Sy - p.y) * invd.y;
+            if (idx >= S.nphot_local) exhausted = true;
+            else {
+                int lo = 0, hi = S.njob - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+                }
+                if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
+                const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
+                g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
+                g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
+                const float4 u = rng4(g);
+                const float4 v = rng4(g);
+                p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
+                if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
+                else p.d = S.src;
+                p.w = 1.0f; p.order = 0; p.direct = true;
+                p.is = S.nslab_z - 1; p.iz = S.nz - 1;
+                p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
+                p.frozen = (S.solver == B200RT_SOLVER_IPA);
+                p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
+                p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
+                if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
+                p.tau = -__logf(v.x);
+                invd = inv_dir(p.d);
+                alive = true;
+                ++n_phot;
+                if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
             }
         }
-        tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
-        const float dexit = fminf(tz, fminf(tx, ty));
-        const float dcol = M > 0.0f ? p.tau / M : RT_INF;
-        const float inv_absdz = fabsf(invd.z);
+        if (!alive) break;       // exhausted and nothing in flight
 
-        if (dcol < dexit) {
-            // ================= tentative collision
-            const float zn = p.z + p.d.z * dcol;
+        // =========================================================== (2) flight: bounded number of cheap steps
+        int ev = EV_NONE;
+#pragma unroll 1
+        for (int kstep = 0; kstep < S.flight_steps && ev == EV_NONE; ++kstep) {
+            const int is = p.is;
+            const int grp = sm.cg[is];
+            const int gcz = sm.g_cz[grp];
+            const bool in3 = gcz >= 0;
+            bool empty = !in3;
+            if (in3) {
+                empty = __ldg(S.empty3 + (size_t(gcz) * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
+                ++n_cell;
+            }
+            // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
+            const int slo = empty ? sm.g_lo[grp] : is;
+            const int shi = empty ? sm.g_lo[grp + 1] : is + 1;
+            const int l0 = sm.lay0[slo], l1 = sm.lay0[shi];
+            const float zlo = sm.z[l0], zhi = sm.z[l1];
+            float M;
+            int ixlo = p.cix, ixhi = p.cix + 1, iylo = p.ciy, iyhi = p.ciy + 1;
+            if (empty) {
+                M = sm.g_maj1d[grp];
+                ixlo = (p.cix >> S.shx) << S.shx; ixhi = ixlo + (1 << S.shx);
+                iylo = (p.ciy >> S.shy) << S.shy; iyhi = iylo + (1 << S.shy);
+            } else {
+                M = sm.maj1d[is] + __ldg(S.maj + (size_t(sm.cz[is]) * S.ncy + p.ciy) * S.ncx + p.cix);
+            }
+            float tz = RT_INF, tx = RT_INF, ty = RT_INF;
+            if (p.d.z > 0.0f) tz = (zhi - p.z) * invd.z; else if (p.d.z < 0.0f) tz = (zlo - p.z) * invd.z;
+            if (in3 && !p.frozen) {
+                if (p.d.x > 0.0f) tx = (fminf(float(ixhi) * S.Sx, S.Lx) - p.x) * invd.x;
+                else if (p.d.x < 0.0f) tx = (float(ixlo) * S.Sx - p.x) * invd.x;
+                if (p.d.y > 0.0f) ty = (fminf(float(iyhi) * S.Sy, S.Ly) - p.y) * invd.y;
+                else if (p.d.y < 0.0f) ty = (float(iylo) * S.Sy - p.y) * invd.y;
+            }
+            tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
+            const float dexit = fminf(tz, fminf(tx, ty));
+            const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
+            const bool hit = dcol < dexit;
+            const float dmove = hit ? dcol : dexit;
+            const bool zcross = !hit && (tz <= tx) && (tz <= ty);
+            const bool xcross = !hit && !zcross && (tx <= ty);
+            const bool ycross = !hit && !zcross && !xcross;
+
+            // ---- move
+            float zn = p.z + p.d.z * dmove;
+            if (zcross) zn = p.d.z > 0.0f ? zhi : zlo;
             int izn = p.iz;
-            if (l1 - l0 > 1) {
-                izn = l0;
-                while (izn < l1 - 1 && zn >= sm.z[izn + 1]) ++izn;
-            }
-            if (J.has_abs) {
-                const float ta = abs_tau(S, sm, p.job, p.z, p.iz, zn, izn, dcol, inv_absdz);
-                const float wn = p.w * __expf(-ta);
+            if (hit || (per_level && J.has_abs)) izn = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
+            if (zcross) izn = p.d.z > 0.0f ? l1 - 1 : l0;
+            if (per_level && J.has_abs) {
+                // flux / heating targets: weight must be current at every level (cells are single layers here)
+                const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + izn) * dmove);
                 w_atm += double(p.w) - double(wn);
                 if (want_heat) {
                     const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
@@ -448,237 +531,275 @@ __global__ void __launch_bounds__(256) transport_kernel(const __grid_constant__ 
                 }
                 p.w = wn;
             }
+            p.leg += dmove;
             if (!p.frozen) {
-                p.x += p.d.x * dcol; p.y += p.d.y * dcol;
-                if (!in3) { p.x = wrapf(p.x, S.Lx); p.y = wrapf(p.y, S.Ly); }
+                p.x += p.d.x * dmove; p.y += p.d.y * dmove;
+                if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
             }
-            p.z = zn; p.iz = izn;
-            const float4 u = rng4(g);
-            float sig = sm.e1tot[izn];
-            float s3 = 0.0f;
-            int fx = 0, fy = 0;
-            size_t vox = 0;
-            if (in3) {
-                if (p.frozen) { fx = p.cix; fy = p.ciy; }
-                else {
-                    fx = min(min(S.nx, (p.cix + 1) * S.svx) - 1, max(p.cix * S.svx, int(p.x * S.inv_dx)));
-                    fy = min(min(S.ny, (p.ciy + 1) * S.svy) - 1, max(p.ciy * S.svy, int(p.y * S.inv_dy)));
+            p.z = zn;
+
+            if (hit) {
+                // ---- tentative collision
+                p.iz = izn;
+                const float4 u = rng4(g);
+                float sig = sm.e1tot[izn];
+                float s3 = 0.0f;
+                int fx = 0, fy = 0;
+                size_t vox = 0;
+                if (in3) {
+                    if (p.frozen) { fx = p.cix; fy = p.ciy; }
+                    else {
+                        fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
+                        fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
+                    }
+                    vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                    if (!empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; ++n_tent; }
                 }
-                vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
-                s3 = __ldg(S.ext3tot + vox);
-                sig += s3;
-                ++n_tent;
-            }
-            p.tau = -__logf(u.y);
-            float uc = u.x * M;
-            if (uc < sig) {
-                // ============= real collision: pick the scattering component (uc is uniform on [0, sig))
-                float omg = 1.0f, apf = 0.0f;
-                bool found = false;
-                if (uc < s3) {
-                    if (S.np3d == 1) {
-                        const float2 pr = __ldg(S.prop3 + vox);
-                        omg = pr.x; apf = pr.y; found = true;
+                p.tau = -__logf(u.y);
+                const float uc = u.x * M;
+                if (uc < sig) {
+                    ev = EV_COLL;
+                    ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox; ev_in3 = in3;
+                    if (in3 && empty && !p.frozen) {
+                        // keep the fine cell indices consistent with the new position inside the coarse cell
+                        p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
+                    }
+                    if (empty && shi - slo > 1) { int s = slo; while (s < shi - 1 && izn >= sm.lay0[s + 1]) ++s; p.is = s; }
+                }
+            } else {
+                p.tau = fmaxf(0.0f, p.tau - M * dexit);
+                if (zcross) {
+                    p.iz = izn;
+                    if (p.d.z > 0.0f) {
+                        if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
+                        if (shi >= S.nslab_z) ev = EV_ESC;
+                        else { p.is = shi; p.iz = l1; }
                     } else {
-                        const size_t n3 = size_t(S.nz3) * nxy;
-                        for (int k = 0; k < S.np3d; ++k) {
-                            const float e = __ldg(S.ext3 + size_t(k) * n3 + vox);
-                            if (uc < e || k == S.np3d - 1) {
-                                const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + vox);
-                                omg = pr.x; apf = pr.y; found = true;
-                                break;
+                        if (want_flux) {
+                            if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
+                            flux_tally(S, J, p, 1, l0, n_tally);
+                        }
+                        if (slo == 0) ev = EV_SFC;
+                        else { p.is = slo - 1; p.iz = l0 - 1; }
+                    }
+                    if (ev == EV_NONE && !p.frozen) {
+                        const bool was3 = in3;
+                        const bool now3 = sm.cz[p.is] >= 0;
+                        if (now3 && (!was3 || empty)) {
+                            // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
+                            p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                            p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+                            if (was3) {   // stay inside the horizontal bounds of the coarse cell just traversed
+                                p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, p.cix));
+                                p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, p.ciy));
                             }
-                            uc -= e;
                         }
                     }
-                } else uc -= s3;
-                if (!found) {
-                    for (int k = 0; k < S.np1d; ++k) {
-                        const float e = sm.e1[k * S.nz + izn];
-                        if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
+                } else {
+                    if (xcross) {
+                        if (p.d.x > 0.0f) { if (ixhi >= S.ncx) { p.cix = 0; p.x = 0.0f; } else { p.cix = ixhi; p.x = float(ixhi) * S.Sx; } }
+                        else { p.x = float(ixlo) * S.Sx; p.cix = ixlo - 1; if (p.cix < 0) { p.cix = S.ncx - 1; p.x = S.Lx; } }
+                        if (empty) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
+                    }
+                    if (ycross) {
+                        if (p.d.y > 0.0f) { if (iyhi >= S.ncy) { p.ciy = 0; p.y = 0.0f; } else { p.ciy = iyhi; p.y = float(iyhi) * S.Sy; } }
+                        else { p.y = float(iylo) * S.Sy; p.ciy = iylo - 1; if (p.ciy < 0) { p.ciy = S.ncy - 1; p.y = S.Ly; } }
+                        if (empty) p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
+                    }
+                    if (empty && shi - slo > 1) {
+                        // left an empty multi-slab coarse cell sideways: find the fine z slab of the current height
+                        int s = slo;
+                        while (s < shi - 1 && p.z >= sm.z[sm.lay0[s + 1]]) ++s;
+                        p.is = s;
+                    }
+                }
+            }
+        }
+        if (ev == EV_NONE) continue;
+
+        // =========================================================== (3) events
+        // ---- path-integrated gas absorption of the leg that ends here
+        const int izb = (ev == EV_SFC) ? 0 : (ev == EV_ESC ? S.nz - 1 : p.iz);
+        if (ev == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; }
+        if (J.has_abs && !per_level) {
+            const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, fabsf(invd.z));
+            const float wn = p.w * __expf(-ta);
+            w_atm += double(p.w) - double(wn);
+            p.w = wn;
+        }
+        p.za = p.z; p.iza = izb; p.leg = 0.0f;
+        if (ev == EV_ESC) { w_toa += double(p.w); alive = false; continue; }
+
+        float4 u;
+        float3 newd;
+        float fac;
+        float apf = 0.0f;
+        int fx = 0, fy = 0;
+        float s3 = 0.0f;
+        int sfc_type = 0;
+        float prm[5];
+        const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
+        if (ev == EV_COLL) {
+            // ---- real collision: pick the scattering component (uc is uniform on [0, sig))
+            u = ev_u;
+            fx = ev_fx; fy = ev_fy; s3 = ev_s3;
+            float uc = ev_uc;
+            const int izn = p.iz;
+            float omg = 1.0f;
+            bool found = false;
+            if (uc < s3) {
+                if (S.np3d == 1) {
+                    const float2 pr = __ldg(S.prop3 + ev_vox);
+                    omg = pr.x; apf = pr.y; found = true;
+                } else {
+                    const size_t n3 = size_t(S.nz3) * nxy;
+                    for (int k = 0; k < S.np3d; ++k) {
+                        const float e = __ldg(S.ext3 + size_t(k) * n3 + ev_vox);
+                        if (uc < e || k == S.np3d - 1) {
+                            const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + ev_vox);
+                            omg = pr.x; apf = pr.y; found = true;
+                            break;
+                        }
                         uc -= e;
                     }
                 }
-                ++n_coll;
-                const float wn = p.w * omg;
-                if (wn < p.w) {
-                    w_atm += double(p.w) - double(wn);
-                    if (want_heat) {
-                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                        tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
-                        ++n_tally;
-                    }
+            } else uc -= s3;
+            if (!found) {
+                for (int k = 0; k < S.np1d; ++k) {
+                    const float e = sm.e1[k * S.nz + izn];
+                    if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
+                    uc -= e;
                 }
-                p.w = wn;
-                p.order++; p.direct = false;
-                if (!(p.w > 0.0f)) { alive = false; continue; }
-                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
-                    if (!in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
-                    else { p.cix = fx; p.ciy = fy; }
-                    p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                    p.frozen = true;
-                }
-                if (want_rad) {
-                    for (int k = 0; k < S.nrad; ++k) {
-                        const DevSensor& se = S.sens[k];
-                        const float dzs = (se.zt - p.z) * se.s.z;
-                        if (!(dzs > 0.0f)) continue;
-                        const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
-                        const float f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
-                        if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
-                    }
-                }
-                float xi_tab = 0.5f;
-                if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
-                const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
-                p.d = rotate_dir(p.d, mu, RT_2PI * u.w);
-                invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
-                invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
-                invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
-                if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
-                if (p.w < S.wmin) {
-                    const float4 v = rng4(g);
-                    if (v.x * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
-                    else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
-                }
-                if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
             }
+            ++n_coll;
+            fac = omg;
         } else {
-            // ================= move to the cell boundary
-            p.tau = fmaxf(0.0f, p.tau - M * dexit);
-            const bool zcross = (tz <= tx && tz <= ty);
-            float zn = p.z + p.d.z * dexit;
-            int izn = p.iz;
-            if (zcross) { zn = p.d.z > 0.0f ? zhi : zlo; izn = p.d.z > 0.0f ? l1 - 1 : l0; }
-            else if (l1 - l0 > 1) { izn = l0; while (izn < l1 - 1 && zn >= sm.z[izn + 1]) ++izn; }
-            if (J.has_abs) {
-                const float ta = abs_tau(S, sm, p.job, p.z, p.iz, zn, izn, dexit, inv_absdz);
-                const float wn = p.w * __expf(-ta);
+            // ---- surface hit
+            ++n_sfc;
+            u = rng4(g);
+            int sx, sy;
+            if (p.frozen) {
+                sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
+                sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
+            } else {
+                sx = min(S.sfc_nx - 1, max(0, int(p.x * S.inv_Lx * float(S.sfc_nx))));
+                sy = min(S.sfc_ny - 1, max(0, int(p.y * S.inv_Ly * float(S.sfc_ny))));
+            }
+            const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
+            sfc_type = __ldg(S.sfc_type + si);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
+            if (want_rad && S.nz3 > 0 && S.iz0 == 0) {
+                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
+            }
+            fac = 1.0f;
+        }
+
+        // ---- weight after the interaction (collision: implicit capture) and book-keeping
+        if (ev == EV_COLL) {
+            const float wn = p.w * fac;
+            if (wn < p.w) {
                 w_atm += double(p.w) - double(wn);
                 if (want_heat) {
                     const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
                     const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                    tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
+                    tally_add(S.heat + (size_t(J.slab) * S.nz + p.iz) * nxy + size_t(hy) * S.nx + hx,
+                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + p.iz) : 1.0));
                     ++n_tally;
                 }
-                p.w = wn;
             }
-            if (!p.frozen) {
-                p.x += p.d.x * dexit; p.y += p.d.y * dexit;
-                if (!in3) { p.x = wrapf(p.x, S.Lx); p.y = wrapf(p.y, S.Ly); }
-            }
-            p.z = zn; p.iz = izn;
-            if (zcross) {
-                if (p.d.z > 0.0f) {
-                    if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
-                    if (is + 1 >= S.nslab_z) { w_toa += double(p.w); alive = false; continue; }
-                    p.is = is + 1; p.iz = l1;
-                } else {
-                    if (want_flux) {
-                        if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
-                        flux_tally(S, J, p, 1, l0, n_tally);
-                    }
-                    if (is > 0) { p.is = is - 1; p.iz = l0 - 1; }
-                }
-                if (is > 0 || p.d.z > 0.0f) {
-                    // entering a 3-D slab from a 1-D slab: locate the coarse cell
-                    if (!in3 && sm.cz[p.is] >= 0 && !p.frozen) {
-                        p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
-                        p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
-                    }
-                } else {
-                    // ============= surface
-                    ++n_sfc;
-                    int sx, sy;
-                    if (p.frozen) {
-                        sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
-                        sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
-                    } else {
-                        sx = min(S.sfc_nx - 1, max(0, int(p.x / S.Lx * float(S.sfc_nx))));
-                        sy = min(S.sfc_ny - 1, max(0, int(p.y / S.Ly * float(S.sfc_ny))));
-                    }
-                    const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
-                    const int type = __ldg(S.sfc_type + si);
-                    float prm[5];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
-                    const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
-                    if (want_rad) {
-                        int fx = 0, fy = 0;
-                        float s3 = 0.0f;
-                        if (S.nz3 > 0 && S.iz0 == 0) {
-                            fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                            fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                            s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
-                        }
-                        for (int k = 0; k < S.nrad; ++k) {
-                            const DevSensor& se = S.sens[k];
-                            if (!(se.s.z > 0.0f) || !(se.zt > p.z)) continue;
-                            const float f = brdf_eval(type, prm, wi, se.s) * se.s.z;
-                            if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
-                        }
-                    }
-                    const float4 u = rng4(g);
-                    float3 wo = make_float3(0.f, 0.f, 1.f);
-                    float fac = 0.0f;
-                    bool diffuse = true;
-                    if (type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
-                    if (diffuse) {
-                        const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
-                        float sp, cp;
-                        __sincosf(RT_2PI * u.y, &sp, &cp);
-                        wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
-                        fac = (type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
-                    } else {
-                        const float sig2 = fmaxf(1e-6f, prm[4]);
-                        const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
-                        float sp, cp;
-                        __sincosf(RT_2PI * u.y, &sp, &cp);
-                        const float zx = r * cp, zy = r * sp;
-                        const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
-                        const float3 n = make_float3(-zx * nn, -zy * nn, nn);
-                        const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
-                        if (cosg > 0.0f) {
-                            wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
-                            if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
-                        }
-                    }
-                    const float wn = p.w * fac;
-                    w_sfc += double(p.w) - double(wn);
-                    p.w = wn;
-                    if (!(p.w > 0.0f)) { alive = false; continue; }
-                    {
-                        const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
-                        p.d = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
-                    }
-                    invd.x = p.d.x != 0.0f ? 1.0f / p.d.x : RT_INF;
-                    invd.y = p.d.y != 0.0f ? 1.0f / p.d.y : RT_INF;
-                    invd.z = p.d.z != 0.0f ? 1.0f / p.d.z : RT_INF;
-                    p.direct = false; p.order++;
-                    p.is = 0; p.iz = 0; p.z = sm.z[0];
-                    if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
-                    if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
-                        p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                        p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                        p.frozen = true;
-                    }
-                    if (p.w < S.wmin) {
-                        if (u.w * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
-                        else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
-                    }
-                    if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
-                }
-            } else if (tx <= ty) {
-                if (p.d.x > 0.0f) { if (p.cix + 1 >= S.ncx) { p.cix = 0; p.x = 0.0f; } else { p.cix++; p.x = float(p.cix) * S.Sx; } }
-                else { p.x = float(p.cix) * S.Sx; p.cix--; if (p.cix < 0) { p.cix = S.ncx - 1; p.x = S.Lx; } }
-            } else {
-                if (p.d.y > 0.0f) { if (p.ciy + 1 >= S.ncy) { p.ciy = 0; p.y = 0.0f; } else { p.ciy++; p.y = float(p.ciy) * S.Sy; } }
-                else { p.y = float(p.ciy) * S.Sy; p.ciy--; if (p.ciy < 0) { p.ciy = S.ncy - 1; p.y = S.Ly; } }
+            p.w = wn;
+            p.order++; p.direct = false;
+            if (!(p.w > 0.0f)) { alive = false; continue; }
+            if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
+                else { p.cix = fx; p.ciy = fy; }
+                p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                p.frozen = true;
             }
         }
+
+        // ---- local estimates toward every sensor (shared by both event kinds)
+        if (want_rad) {
+            for (int k = 0; k < S.nrad; ++k) {
+                const DevSensor& se = S.sens[k];
+                const float dzs = (se.zt - p.z) * se.s.z;
+                if (!(dzs > 0.0f)) continue;
+                float f;
+                if (ev == EV_COLL) {
+                    const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
+                    f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
+                } else {
+                    f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm, wi, se.s) * se.s.z : 0.0f;
+                }
+                if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
+            }
+        }
+
+        // ---- new direction
+        if (ev == EV_COLL) {
+            float xi_tab = 0.5f;
+            if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
+            const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
+            newd = rotate_dir(p.d, mu, RT_2PI * u.w);
+            if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
+        } else {
+            float3 wo = make_float3(0.f, 0.f, 1.f);
+            fac = 0.0f;
+            bool diffuse = true;
+            if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
+            if (diffuse) {
+                const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
+                float sp, cp;
+                __sincosf(RT_2PI * u.y, &sp, &cp);
+                wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
+                fac = (sfc_type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
+            } else {
+                const float sig2 = fmaxf(1e-6f, prm[4]);
+                const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
+                float sp, cp;
+                __sincosf(RT_2PI * u.y, &sp, &cp);
+                const float zx = r * cp, zy = r * sp;
+                const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
+                const float3 n = make_float3(-zx * nn, -zy * nn, nn);
+                const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
+                if (cosg > 0.0f) {
+                    wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
+                    if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
+                }
+            }
+            const float wn = p.w * fac;
+            w_sfc += double(p.w) - double(wn);
+            p.w = wn;
+            if (!(p.w > 0.0f)) { alive = false; continue; }
+            const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
+            newd = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
+            p.direct = false; p.order++;
+        }
+        p.d = newd;
+        invd = inv_dir(p.d);
+        if (ev == EV_SFC) {
+            if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
+            if (S.nz3 > 0 && S.iz0 == 0 && !p.frozen) {
+                p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+            }
+            if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                p.frozen = true;
+            }
+        }
+        // ---- Russian roulette (Pho_wmin / Pho_wfac), shared
+        if (p.w < S.wmin) {
+            float xi = u.w;
+            if (ev == EV_COLL) { const float4 v = rng4(g); xi = v.x; }
+            if (xi * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
+            else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
+        }
+        if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
     }
 
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
@@ -750,7 +871,7 @@ struct Handle {
     size_t smem_bytes = 0;
     // owned device memory
     std::vector<DevBuf*> pool;
-    DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d;
+    DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3;
     DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
     DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
     DevBuf flux, rad, heat;
@@ -852,6 +973,7 @@ int b200rt_destroy(void* handle) {
     if (!H) return B200RT_ERR_ARG;
     cudaSetDevice(H->device);
     DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
+                     &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3,
                      &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
                      &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
                      &H->flux, &H->rad, &H->heat};
@@ -909,13 +1031,22 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
 
     // ------------------------------------------------ super-voxel grid
     const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0;
-    int svx = opt->svx > 0 ? opt->svx : 4, svy = opt->svy > 0 ? opt->svy : 4, svz = opt->svz > 0 ? opt->svz : (nz3 > 16 ? 4 : 1);
+    int svx = opt->svx > 0 ? opt->svx : 2, svy = opt->svy > 0 ? opt->svy : 2, svz = opt->svz > 0 ? opt->svz : (nz3 > 16 ? 4 : 1);
     if (opt->solver != B200RT_SOLVER_3D) { svx = 1; svy = 1; }     // column-frozen modes need cell == column
     if (per_level) svz = 1;                                       // every z crossing must be a level crossing
+    // coarse (emptiness) level: 2^shx x 2^shy fine cells horizontally, cmz fine slabs vertically
+    auto log2floor = [](int v) { int s = 0; while ((2 << s) <= v) ++s; return s; };
+    int shx = log2floor(std::max(1, opt->cmx > 0 ? opt->cmx : 4)), shy = log2floor(std::max(1, opt->cmy > 0 ? opt->cmy : 4));
+    int cmz = opt->cmz > 0 ? opt->cmz : 8;
+    if (per_level) { shx = 0; shy = 0; cmz = 1; }
+    S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 3;
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
     S.Sx = float(sc->dx * svx); S.Sy = float(sc->dy * svy); S.inv_Sx = 1.0f / S.Sx; S.inv_Sy = 1.0f / S.Sy;
+    S.inv_Lx = 1.0f / S.Lx; S.inv_Ly = 1.0f / S.Ly;
+    S.shx = shx; S.shy = shy;
+    S.nCx = (S.ncx + (1 << shx) - 1) >> shx; S.nCy = (S.ncy + (1 << shy) - 1) >> shy;
 
     // ------------------------------------------------ 1-D tables
     std::vector<float> fz(nz + 1), fe1tot(nz, 0.f), fe1cum(nz + 1, 0.f), fe1(e1.size()), fo1(e1.size()), fa1(e1.size());
@@ -948,14 +1079,41 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     }
     S.nslab_z = int(czv.size());
     lay0.push_back(nz);
+    // coarse z groups: runs of 1-D slabs are merged into one group each (unless every level must be visited);
+    // the 3-D block is cut into groups of cmz fine slabs.  A group never mixes 1-D and 3-D slabs.
+    std::vector<int> cg(S.nslab_z), g_lo, g_cz, gz_lo;
+    std::vector<float> g_maj1d;
+    {
+        int ncoarse3 = 0;
+        for (int s = 0; s < S.nslab_z;) {
+            int e = s + 1;
+            if (czv[s] < 0) { if (!per_level) while (e < S.nslab_z && czv[e] < 0) ++e; }
+            else while (e < S.nslab_z && czv[e] >= 0 && (czv[e] / cmz) == (czv[s] / cmz)) ++e;
+            const int gid = int(g_lo.size());
+            g_lo.push_back(s);
+            if (czv[s] >= 0) { g_cz.push_back(ncoarse3++); gz_lo.push_back(czv[s]); } else g_cz.push_back(-1);
+            float m = 0.f;
+            for (int q = s; q < e; ++q) { cg[q] = gid; m = std::max(m, maj1d[q]); }
+            g_maj1d.push_back(m);
+            s = e;
+        }
+        g_lo.push_back(S.nslab_z);
+        gz_lo.push_back(S.ncz);
+        S.ngroup = int(g_cz.size());
+    }
     if ((rc = upload(H, H->zgrd, fz)) || (rc = upload(H, H->e1tot, fe1tot)) || (rc = upload(H, H->e1cum, fe1cum)) ||
         (rc = upload(H, H->e1, fe1)) || (rc = upload(H, H->o1, fo1)) || (rc = upload(H, H->a1, fa1)) ||
-        (rc = upload(H, H->slab_lay0, lay0)) || (rc = upload(H, H->slab_cz, czv)) || (rc = upload(H, H->slab_maj1d, maj1d)))
+        (rc = upload(H, H->slab_lay0, lay0)) || (rc = upload(H, H->slab_cz, czv)) || (rc = upload(H, H->slab_maj1d, maj1d)) ||
+        (rc = upload(H, H->slab_cg, cg)) || (rc = upload(H, H->group_lo, g_lo)) || (rc = upload(H, H->group_cz, g_cz)) ||
+        (rc = upload(H, H->group_maj1d, g_maj1d)) || (rc = upload(H, H->gz_lo, gz_lo)))
         return rc;
+    S.slab_cg = (const int*)H->slab_cg.p; S.group_lo = (const int*)H->group_lo.p; S.group_cz = (const int*)H->group_cz.p;
+    S.group_maj1d = (const float*)H->group_maj1d.p;
     S.zgrd = (const float*)H->zgrd.p; S.e1tot = (const float*)H->e1tot.p; S.e1cum = (const float*)H->e1cum.p;
     S.e1 = (const float*)H->e1.p; S.o1 = (const float*)H->o1.p; S.a1 = (const float*)H->a1.p;
     S.slab_lay0 = (const int*)H->slab_lay0.p; S.slab_cz = (const int*)H->slab_cz.p; S.slab_maj1d = (const float*)H->slab_maj1d.p;
-    H->smem_bytes = sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz + S.nslab_z) + sizeof(int) * (2 * size_t(S.nslab_z) + 1);
+    H->smem_bytes = sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz + S.nslab_z + S.ngroup) +
+                    sizeof(int) * (3 * size_t(S.nslab_z) + 1 + 2 * size_t(S.ngroup) + 1);
     if (H->smem_bytes > 200 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
 
     // ------------------------------------------------ 3-D block
@@ -963,7 +1121,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         const size_t nvox = size_t(nz3) * sc->ny * sc->nx;
         const size_t nall = nvox * sc->np3d;
         if ((rc = dev_alloc(H, H->ext3tot, nvox * 4)) || (rc = dev_alloc(H, H->prop3, nall * 8)) ||
-            (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
+            (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->empty3, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1))) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
             (rc = dev_alloc(H, H->flag, 16)))
             return rc;
         // stage the caller's arrays on the device when they are host pointers
@@ -993,6 +1151,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         pack_scene_kernel<<<nb, 256>>>(de, dom, da, sc->np3d, nvox, (float*)H->ext3tot.p, (float2*)H->prop3.p, (int*)H->flag.p);
         const int ncell = S.ncx * S.ncy * S.ncz;
         majorant_kernel<<<(ncell + 127) / 128, 128>>>((const float*)H->ext3tot.p, sc->nx, sc->ny, nz3, svx, svy, svz, S.ncx, S.ncy, S.ncz, (float*)H->maj.p);
+        const int nC = S.nCx * S.nCy * int(gz_lo.size() - 1);
+        empty_kernel<<<(nC + 127) / 128, 128>>>((const float*)H->maj.p, S.ncx, S.ncy, shx, shy, S.nCx, S.nCy, int(gz_lo.size() - 1),
+                                                 (const int*)H->gz_lo.p, (unsigned char*)H->empty3.p);
         const int ncol = sc->nx * sc->ny;
         tau_up_kernel<<<(ncol + 127) / 128, 128>>>((const float*)H->ext3tot.p, S.zgrd, iz0, sc->nx, sc->ny, nz3, (float*)H->tu3.p);
         CK(cudaGetLastError());
@@ -1002,7 +1163,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (bad) return fail(H, B200RT_ERR_ARG, "3-D field out of range (need ext >= 0, 0 <= omg <= 1, finite apf)");
         S.ext3tot = (const float*)H->ext3tot.p; S.prop3 = (const float2*)H->prop3.p; S.ext3 = (const float*)H->ext3.p;
-        S.maj = (const float*)H->maj.p; S.tu3 = (const float*)H->tu3.p;
+        S.maj = (const float*)H->maj.p; S.tu3 = (const float*)H->tu3.p; S.empty3 = (const unsigned char*)H->empty3.p;
     }
 
     // ------------------------------------------------ phase tables (built in fp64 on the host, stored fp32)
@@ -1076,6 +1237,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         se.s = make_float3(view.x == 0.f ? 0.f : -view.x, view.y == 0.f ? 0.f : -view.y, -view.z);
         if (std::fabs(se.s.z) < 1e-3f) return fail(H, B200RT_ERR_ARG, "horizontal viewing direction is not supported");
         se.inv_sz = 1.0f / std::fabs(se.s.z);
+        se.inv_szs = 1.0f / se.s.z;
         se.zt = float(std::min(zg[nz], std::max(zg[0], q.zloc)));
         se.zref = float(q.zref);
         se.lt = 0;

@@ -75,7 +75,8 @@ class mcarats_ng:
                  reduce=None,
                  extra_sensors=None,
                  solver_obj=None,
-                 wmin=None):
+                 wmin=None,
+                 dry_run=False):
 
         add_reference(self.reference)
 
@@ -114,6 +115,7 @@ class mcarats_ng:
         self.extra_sensors = list(extra_sensors) if extra_sensors else []
         self._solver_obj = solver_obj
         self._wmin = wmin
+        self.dry_run = dry_run
         self.atm_1ds = atm_1ds
         self.atm_3ds = atm_3ds
 
@@ -386,11 +388,19 @@ class mcarats_ng:
         wmin = DEFAULTS['Pho_wmin'] if self._wmin is None else self._wmin
         opt = abi.make_options(solver=solvers[self.solver], target=tflag, nslab=nslab, shard_rank=self.shard[0], shard_world=self.shard[1],
                                sv=self.supervoxel, iso_ss=DEFAULTS['Pho_iso_SS'], iso_max=DEFAULTS['Pho_iso_max'], wmin=wmin, wfac=DEFAULTS['Pho_wfac'])
+        jobs_args = dict(nphot=nphot, seeds=seeds, slabs=slabs, abs1d=abs1d, flx_scale=fsc, rad_scale=rsc)
+        self.options, self.jobs_args, self.nslab = opt, jobs_args, nslab
+        if self.dry_run:
+            # everything is prepared (scene, options, jobs) but nothing is traced; used by bench.py to time the
+            # device-resident path separately from the host-side packing
+            self.fused = {}
+            return
         own = self._solver_obj is None
         sol = Solver(device=self.device) if own else self._solver_obj
         try:
             sol.upload_scene(scene, opt)
             jobs, keep = abi.make_jobs(nphot, seeds, slabs, abs1d=abs1d, flx_scale=fsc, rad_scale=rsc)
+            self.h2d_bytes = scene.nbytes() + sum(a.nbytes for a in keep)
             sol.run(jobs)
             if self.reduce is not None:
                 res = self.reduce(sol)          # multi-GPU: all-reduce of the tallies (er3t_b200.dist.allreduce_results)
