@@ -61,7 +61,9 @@ struct DevScene {
     int nslab_z;
     int ngroup;               // coarse z groups of fine slabs
     int nCx, nCy, shx, shy;   // coarse (emptiness) grid: 2^shx x 2^shy fine cells per coarse cell
-    int flight_steps;
+    int flight_steps;         // max cell crossings per lane between two event phases
+    int event_min;            // parked lanes that end the flight loop early
+    int regen_min;            // dead lanes that trigger a regeneration
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
     const float* e1tot;       // [nz]
@@ -211,7 +213,7 @@ struct Photon {
     bool direct, frozen;
 };
 
-enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3 };
+enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3, EV_TENT = 4 };
 
 __device__ __forceinline__ float wrapf(float x, float L, float invL) {
     x -= L * floorf(x * invL);
@@ -368,10 +370,13 @@ __device__ __forceinline__ float3 inv_dir(const float3 d) {
 }
 
 // Persistent-thread photon transport.  Every thread owns one photon at a time and regenerates it in place from a
-// global atomic counter.  The body is organised in warp-convergent PHASES to fight divergence:
-//   (1) regeneration of all dead lanes,
-//   (2) a bounded flight loop (cheap, branch-light cell crossings + null collisions on the two-level majorant grid),
-//   (3) one event phase shared by real collisions and surface hits (local estimates, new direction, roulette).
+// global atomic counter (queue-based path regeneration).  To fight divergence the body runs in warp-convergent
+// PHASES, and a phase is only entered when enough lanes of the warp are waiting for it:
+//   (1) regeneration      when >= regen_min lanes are dead (or nothing is in flight),
+//   (2) flight            pure geometry on the two-level majorant grid (no RNG, no 3-D look-ups); lanes that reach a
+//                         tentative collision / the surface / TOA park, the loop ends when >= event_min lanes are parked,
+//   (3) tentative phase   Philox draw + voxel extinction look-up + null-collision rejection for all parked lanes,
+//   (4) event phase       shared by real collisions and surface hits: local estimates, new direction, roulette.
 __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float smem_f[];
     Smem sm;
@@ -402,6 +407,8 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
     }
     __syncthreads();
 
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const bool want_flux = (S.target & B200RT_TARGET_FLUX) != 0;
     const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
     const bool want_heat = (S.target & B200RT_TARGET_HEATING) != 0;
@@ -417,389 +424,413 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
     float3 invd = make_float3(0.f, 0.f, 0.f);
     bool alive = false;
     bool exhausted = false;
+    bool stale = false;          // p.is may not be the fine slab of p.z (after sideways moves in empty coarse cells)
+    int ev = EV_NONE;
     p.job = -1;
     g.c3 = 0xB200u;
-    // collision hand-off from the flight loop to the event phase
-    float ev_s3 = 0.0f, ev_uc = 0.0f;
+    // hand-off from the flight loop to the tentative / event phases
+    float ev_M = 0.0f, ev_s3 = 0.0f, ev_uc = 0.0f;
     float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
     int ev_fx = 0, ev_fy = 0;
     size_t ev_vox = 0;
-    bool ev_in3 = false;
+    bool ev_in3 = false, ev_empty = false;
 
     for (;;) {
-        // =========================================================== (1) regeneration
-        if (!alive && !exhausted) {
-            const unsigned mask = __activemask();
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(mask) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(S.counter, (unsigned long long)__popc(mask));
-            base = __shfl_sync(mask, base, leader);
-            const unsigned long long idx = base + __popc(mask & ((1u << lane) - 1u));
-            if (idx >= S.nphot_local) exhausted = true;
-            else {
-                int lo = 0, hi = S.njob - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+        // =========================================================== (1) regeneration (batched)
+        {
+            const bool need = !alive && !exhausted;
+            const unsigned mneed = __ballot_sync(FULL, need);
+            const unsigned malive = __ballot_sync(FULL, alive);
+            if (mneed != 0u && (__popc(mneed) >= S.regen_min || malive == 0u)) {
+                unsigned long long base = 0;
+                const int leader = __ffs(mneed) - 1;
+                if (lane == leader) base = atomicAdd(S.counter, (unsigned long long)__popc(mneed));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    const unsigned long long idx = base + __popc(mneed & ((1u << lane) - 1u));
+                    if (idx >= S.nphot_local) exhausted = true;
+                    else {
+                        int lo = 0, hi = S.njob - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+                        }
+                        if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
+                        const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
+                        g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
+                        g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
+                        const float4 u = rng4(g);
+                        const float4 v = rng4(g);
+                        p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
+                        if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
+                        else p.d = S.src;
+                        p.w = 1.0f; p.order = 0; p.direct = true;
+                        p.is = S.nslab_z - 1; p.iz = S.nz - 1;
+                        p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
+                        p.frozen = (S.solver == B200RT_SOLVER_IPA);
+                        p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
+                        p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
+                        if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
+                        p.tau = -__logf(v.x);
+                        invd = inv_dir(p.d);
+                        alive = true; stale = false; ev = EV_NONE;
+                        ++n_phot;
+                        if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
+                    }
                 }
-                if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
-                const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
-                g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
-                g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
-                const float4 u = rng4(g);
-                const float4 v = rng4(g);
-                p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
-                if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
-                else p.d = S.src;
-                p.w = 1.0f; p.order = 0; p.direct = true;
-                p.is = S.nslab_z - 1; p.iz = S.nz - 1;
-                p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
-                p.frozen = (S.solver == B200RT_SOLVER_IPA);
-                p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
-                p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
-                if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
-                p.tau = -__logf(v.x);
-                invd = inv_dir(p.d);
-                alive = true;
-                ++n_phot;
-                if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
             }
+            if (__ballot_sync(FULL, alive) == 0u && __ballot_sync(FULL, !exhausted) == 0u) break;
         }
-        if (!alive) break;       // exhausted and nothing in flight
 
-        // =========================================================== (2) flight: bounded number of cheap steps
-        int ev = EV_NONE;
+        // =========================================================== (2) flight: geometry only
 #pragma unroll 1
-        for (int kstep = 0; kstep < S.flight_steps && ev == EV_NONE; ++kstep) {
-            const int is = p.is;
-            const int grp = sm.cg[is];
-            const int gcz = sm.g_cz[grp];
-            const bool in3 = gcz >= 0;
-            bool empty = !in3;
-            if (in3) {
-                empty = __ldg(S.empty3 + (size_t(gcz) * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
-                ++n_cell;
-            }
-            // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
-            const int slo = empty ? sm.g_lo[grp] : is;
-            const int shi = empty ? sm.g_lo[grp + 1] : is + 1;
-            const int l0 = sm.lay0[slo], l1 = sm.lay0[shi];
-            const float zlo = sm.z[l0], zhi = sm.z[l1];
-            float M;
-            int ixlo = p.cix, ixhi = p.cix + 1, iylo = p.ciy, iyhi = p.ciy + 1;
-            if (empty) {
-                M = sm.g_maj1d[grp];
-                ixlo = (p.cix >> S.shx) << S.shx; ixhi = ixlo + (1 << S.shx);
-                iylo = (p.ciy >> S.shy) << S.shy; iyhi = iylo + (1 << S.shy);
-            } else {
-                M = sm.maj1d[is] + __ldg(S.maj + (size_t(sm.cz[is]) * S.ncy + p.ciy) * S.ncx + p.cix);
-            }
-            float tz = RT_INF, tx = RT_INF, ty = RT_INF;
-            if (p.d.z > 0.0f) tz = (zhi - p.z) * invd.z; else if (p.d.z < 0.0f) tz = (zlo - p.z) * invd.z;
-            if (in3 && !p.frozen) {
-                if (p.d.x > 0.0f) tx = (fminf(float(ixhi) * S.Sx, S.Lx) - p.x) * invd.x;
-                else if (p.d.x < 0.0f) tx = (float(ixlo) * S.Sx - p.x) * invd.x;
-                if (p.d.y > 0.0f) ty = (fminf(float(iyhi) * S.Sy, S.Ly) - p.y) * invd.y;
-                else if (p.d.y < 0.0f) ty = (float(iylo) * S.Sy - p.y) * invd.y;
-            }
-            tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
-            const float dexit = fminf(tz, fminf(tx, ty));
-            const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
-            const bool hit = dcol < dexit;
-            const float dmove = hit ? dcol : dexit;
-            const bool zcross = !hit && (tz <= tx) && (tz <= ty);
-            const bool xcross = !hit && !zcross && (tx <= ty);
-            const bool ycross = !hit && !zcross && !xcross;
-
-            // ---- move
-            float zn = p.z + p.d.z * dmove;
-            if (zcross) zn = p.d.z > 0.0f ? zhi : zlo;
-            int izn = p.iz;
-            if (hit || (per_level && J.has_abs)) izn = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
-            if (zcross) izn = p.d.z > 0.0f ? l1 - 1 : l0;
-            if (per_level && J.has_abs) {
-                // flux / heating targets: weight must be current at every level (cells are single layers here)
-                const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + izn) * dmove);
-                w_atm += double(p.w) - double(wn);
-                if (want_heat) {
-                    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                    tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
-                    ++n_tally;
+        for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
+            if (alive && ev == EV_NONE) {
+                int is = p.is;
+                const int grp = sm.cg[is];
+                const int gcz = sm.g_cz[grp];
+                const bool in3 = gcz >= 0;
+                bool empty = !in3;
+                if (in3) {
+                    empty = __ldg(S.empty3 + (size_t(gcz) * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
+                    ++n_cell;
                 }
+                if (!empty && stale) {
+                    // entered a non-empty coarse cell sideways: find the fine z slab of the current height
+                    int lo = sm.g_lo[grp], hi = sm.g_lo[grp + 1] - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (p.z >= sm.z[sm.lay0[mid]]) lo = mid; else hi = mid - 1;
+                    }
+                    is = lo; p.is = lo;
+                }
+                if (!empty) stale = false;
+                // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
+                const int slo = empty ? sm.g_lo[grp] : is;
+                const int shi = empty ? sm.g_lo[grp + 1] : is + 1;
+                const int l0 = sm.lay0[slo], l1 = sm.lay0[shi];
+                const float zlo = sm.z[l0], zhi = sm.z[l1];
+                const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
+                const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
+                const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
+                float M;
+                if (empty) M = sm.g_maj1d[grp];
+                else M = sm.maj1d[is] + __ldg(S.maj + (size_t(sm.cz[is]) * S.ncy + p.ciy) * S.ncx + p.cix);
+                // distances to the cell faces along the flight direction (branch-free)
+                const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
+                float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
+                if (p.d.z == 0.0f) tz = RT_INF;
+                float tx = RT_INF, ty = RT_INF;
+                if (in3 && !p.frozen) {
+                    tx = ((upx ? fminf(float(ixhi) * S.Sx, S.Lx) : float(ixlo) * S.Sx) - p.x) * invd.x;
+                    ty = ((upy ? fminf(float(iyhi) * S.Sy, S.Ly) : float(iylo) * S.Sy) - p.y) * invd.y;
+                    if (p.d.x == 0.0f) tx = RT_INF;
+                    if (p.d.y == 0.0f) ty = RT_INF;
+                }
+                tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
+                const float dexit = fminf(tz, fminf(tx, ty));
+                const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
+                const bool hit = dcol < dexit;
+                const float dmove = hit ? dcol : dexit;
+                const bool zcross = !hit && (tz <= tx) && (tz <= ty);
+                const bool xcross = !hit && !zcross && (tx <= ty);
+                const bool ycross = !hit && !zcross && !xcross;
+
+                // ---- move
+                float zn = p.z + p.d.z * dmove;
+                if (zcross) zn = upz ? zhi : zlo;
+                if (per_level && J.has_abs) {
+                    // flux / heating targets: weight must be current at every level (cells are single layers here)
+                    const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + l0) * dmove);
+                    w_atm += double(p.w) - double(wn);
+                    if (want_heat) {
+                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                        tally_add(S.heat + (size_t(J.slab) * S.nz + l0) * nxy + size_t(hy) * S.nx + hx,
+                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + l0) : 1.0));
+                        ++n_tally;
+                    }
+                    p.w = wn;
+                }
+                p.leg += dmove;
+                if (!p.frozen) {
+                    p.x += p.d.x * dmove; p.y += p.d.y * dmove;
+                    if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
+                }
+                p.z = zn;
+
+                if (hit) {
+                    // park at the tentative collision point; the RNG / look-up work is done in phase (3)
+                    ev = EV_TENT;
+                    ev_M = M; ev_in3 = in3; ev_empty = empty;
+                    p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
+                } else {
+                    p.tau = fmaxf(0.0f, p.tau - M * dexit);
+                    if (zcross) {
+                        stale = false;
+                        if (upz) {
+                            p.iz = l1 - 1;
+                            if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
+                            if (shi >= S.nslab_z) ev = EV_ESC;
+                            else { p.is = shi; p.iz = l1; }
+                        } else {
+                            p.iz = l0;
+                            if (want_flux) {
+                                if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
+                                flux_tally(S, J, p, 1, l0, n_tally);
+                            }
+                            if (slo == 0) ev = EV_SFC;
+                            else { p.is = slo - 1; p.iz = l0 - 1; }
+                        }
+                        if (ev == EV_NONE && !p.frozen && sm.cz[p.is] >= 0 && (!in3 || empty)) {
+                            // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
+                            int cx = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                            int cy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+                            if (in3) {   // stay inside the horizontal bounds of the coarse cell just traversed
+                                cx = min(min(S.ncx, ixhi) - 1, max(ixlo, cx));
+                                cy = min(min(S.ncy, iyhi) - 1, max(iylo, cy));
+                            }
+                            p.cix = cx; p.ciy = cy;
+                        }
+                    } else {
+                        // sideways crossing (cyclic domain); branch-free selects
+                        const bool px = xcross;
+                        const bool up = px ? upx : upy;
+                        const int nc = px ? S.ncx : S.ncy;
+                        const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
+                        const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
+                        int ci = up ? ihi : ilo - 1;
+                        float pos = up ? float(ihi) * Sc : float(ilo) * Sc;
+                        if (ci >= nc) { ci = 0; pos = 0.0f; }
+                        if (ci < 0) { ci = nc - 1; pos = L; }
+                        if (px) { p.cix = ci; p.x = pos; } else { p.ciy = ci; p.y = pos; }
+                        if (empty) {
+                            // the other index follows the position inside the coarse cell that was crossed
+                            if (px) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
+                            else p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
+                            stale = (shi - slo > 1);
+                        }
+                    }
+                }
+            }
+            const unsigned parked = __ballot_sync(FULL, alive && ev != EV_NONE);
+            const unsigned flying = __ballot_sync(FULL, alive && ev == EV_NONE);
+            if (__popc(parked) >= S.event_min || flying == 0u) break;
+        }
+
+        // =========================================================== (3) tentative collisions: accept or reject
+        if (alive && ev == EV_TENT) {
+            const float4 u = rng4(g);
+            const int izn = p.iz;
+            float sig = sm.e1tot[izn];
+            float s3 = 0.0f;
+            int fx = 0, fy = 0;
+            size_t vox = 0;
+            if (ev_in3) {
+                if (p.frozen) { fx = p.cix; fy = p.ciy; }
+                else {
+                    const int shx = ev_empty ? S.shx : 0, shy = ev_empty ? S.shy : 0;
+                    const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
+                    const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
+                    fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
+                    fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
+                }
+                vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; ++n_tent; }
+            }
+            p.tau = -__logf(u.y);
+            const float uc = u.x * ev_M;
+            if (uc < sig) {
+                ev = EV_COLL;
+                ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox;
+                if (ev_in3 && ev_empty && !p.frozen) {
+                    // keep the fine cell indices consistent with the position inside the coarse cell
+                    p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
+                }
+            } else ev = EV_NONE;
+        }
+
+        // =========================================================== (4) events
+        if (alive && ev != EV_NONE) {
+            const int evk = ev;
+            ev = EV_NONE;
+            // ---- path-integrated gas absorption of the leg that ends here
+            const int izb = (evk == EV_SFC) ? 0 : (evk == EV_ESC ? S.nz - 1 : p.iz);
+            if (evk == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; stale = false; }
+            if (J.has_abs && !per_level) {
+                const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, fabsf(invd.z));
+                const float wn = p.w * __expf(-ta);
+                w_atm += double(p.w) - double(wn);
                 p.w = wn;
             }
-            p.leg += dmove;
-            if (!p.frozen) {
-                p.x += p.d.x * dmove; p.y += p.d.y * dmove;
-                if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
-            }
-            p.z = zn;
+            p.za = p.z; p.iza = izb; p.leg = 0.0f;
+            if (evk == EV_ESC) { w_toa += double(p.w); alive = false; continue; }
 
-            if (hit) {
-                // ---- tentative collision
-                p.iz = izn;
-                const float4 u = rng4(g);
-                float sig = sm.e1tot[izn];
-                float s3 = 0.0f;
-                int fx = 0, fy = 0;
-                size_t vox = 0;
-                if (in3) {
-                    if (p.frozen) { fx = p.cix; fy = p.ciy; }
-                    else {
-                        fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
-                        fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
-                    }
-                    vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
-                    if (!empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; ++n_tent; }
-                }
-                p.tau = -__logf(u.y);
-                const float uc = u.x * M;
-                if (uc < sig) {
-                    ev = EV_COLL;
-                    ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox; ev_in3 = in3;
-                    if (in3 && empty && !p.frozen) {
-                        // keep the fine cell indices consistent with the new position inside the coarse cell
-                        p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
-                    }
-                    if (empty && shi - slo > 1) { int s = slo; while (s < shi - 1 && izn >= sm.lay0[s + 1]) ++s; p.is = s; }
-                }
-            } else {
-                p.tau = fmaxf(0.0f, p.tau - M * dexit);
-                if (zcross) {
-                    p.iz = izn;
-                    if (p.d.z > 0.0f) {
-                        if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
-                        if (shi >= S.nslab_z) ev = EV_ESC;
-                        else { p.is = shi; p.iz = l1; }
+            float4 u;
+            float3 newd;
+            float apf = 0.0f;
+            int fx = 0, fy = 0;
+            float s3 = 0.0f;
+            int sfc_type = 0;
+            float prm[5];
+            const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
+            if (evk == EV_COLL) {
+                // ---- real collision: pick the scattering component (uc is uniform on [0, sig))
+                u = ev_u;
+                fx = ev_fx; fy = ev_fy; s3 = ev_s3;
+                float uc = ev_uc;
+                const int izn = p.iz;
+                float omg = 1.0f;
+                bool found = false;
+                if (uc < s3) {
+                    if (S.np3d == 1) {
+                        const float2 pr = __ldg(S.prop3 + ev_vox);
+                        omg = pr.x; apf = pr.y; found = true;
                     } else {
-                        if (want_flux) {
-                            if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
-                            flux_tally(S, J, p, 1, l0, n_tally);
-                        }
-                        if (slo == 0) ev = EV_SFC;
-                        else { p.is = slo - 1; p.iz = l0 - 1; }
-                    }
-                    if (ev == EV_NONE && !p.frozen) {
-                        const bool was3 = in3;
-                        const bool now3 = sm.cz[p.is] >= 0;
-                        if (now3 && (!was3 || empty)) {
-                            // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
-                            p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
-                            p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
-                            if (was3) {   // stay inside the horizontal bounds of the coarse cell just traversed
-                                p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, p.cix));
-                                p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, p.ciy));
+                        const size_t n3 = size_t(S.nz3) * nxy;
+                        for (int k = 0; k < S.np3d; ++k) {
+                            const float e = __ldg(S.ext3 + size_t(k) * n3 + ev_vox);
+                            if (uc < e || k == S.np3d - 1) {
+                                const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + ev_vox);
+                                omg = pr.x; apf = pr.y; found = true;
+                                break;
                             }
+                            uc -= e;
                         }
                     }
-                } else {
-                    if (xcross) {
-                        if (p.d.x > 0.0f) { if (ixhi >= S.ncx) { p.cix = 0; p.x = 0.0f; } else { p.cix = ixhi; p.x = float(ixhi) * S.Sx; } }
-                        else { p.x = float(ixlo) * S.Sx; p.cix = ixlo - 1; if (p.cix < 0) { p.cix = S.ncx - 1; p.x = S.Lx; } }
-                        if (empty) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
-                    }
-                    if (ycross) {
-                        if (p.d.y > 0.0f) { if (iyhi >= S.ncy) { p.ciy = 0; p.y = 0.0f; } else { p.ciy = iyhi; p.y = float(iyhi) * S.Sy; } }
-                        else { p.y = float(iylo) * S.Sy; p.ciy = iylo - 1; if (p.ciy < 0) { p.ciy = S.ncy - 1; p.y = S.Ly; } }
-                        if (empty) p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
-                    }
-                    if (empty && shi - slo > 1) {
-                        // left an empty multi-slab coarse cell sideways: find the fine z slab of the current height
-                        int s = slo;
-                        while (s < shi - 1 && p.z >= sm.z[sm.lay0[s + 1]]) ++s;
-                        p.is = s;
-                    }
-                }
-            }
-        }
-        if (ev == EV_NONE) continue;
-
-        // =========================================================== (3) events
-        // ---- path-integrated gas absorption of the leg that ends here
-        const int izb = (ev == EV_SFC) ? 0 : (ev == EV_ESC ? S.nz - 1 : p.iz);
-        if (ev == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; }
-        if (J.has_abs && !per_level) {
-            const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, fabsf(invd.z));
-            const float wn = p.w * __expf(-ta);
-            w_atm += double(p.w) - double(wn);
-            p.w = wn;
-        }
-        p.za = p.z; p.iza = izb; p.leg = 0.0f;
-        if (ev == EV_ESC) { w_toa += double(p.w); alive = false; continue; }
-
-        float4 u;
-        float3 newd;
-        float fac;
-        float apf = 0.0f;
-        int fx = 0, fy = 0;
-        float s3 = 0.0f;
-        int sfc_type = 0;
-        float prm[5];
-        const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
-        if (ev == EV_COLL) {
-            // ---- real collision: pick the scattering component (uc is uniform on [0, sig))
-            u = ev_u;
-            fx = ev_fx; fy = ev_fy; s3 = ev_s3;
-            float uc = ev_uc;
-            const int izn = p.iz;
-            float omg = 1.0f;
-            bool found = false;
-            if (uc < s3) {
-                if (S.np3d == 1) {
-                    const float2 pr = __ldg(S.prop3 + ev_vox);
-                    omg = pr.x; apf = pr.y; found = true;
-                } else {
-                    const size_t n3 = size_t(S.nz3) * nxy;
-                    for (int k = 0; k < S.np3d; ++k) {
-                        const float e = __ldg(S.ext3 + size_t(k) * n3 + ev_vox);
-                        if (uc < e || k == S.np3d - 1) {
-                            const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + ev_vox);
-                            omg = pr.x; apf = pr.y; found = true;
-                            break;
-                        }
+                } else uc -= s3;
+                if (!found) {
+                    for (int k = 0; k < S.np1d; ++k) {
+                        const float e = sm.e1[k * S.nz + izn];
+                        if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
                         uc -= e;
                     }
                 }
-            } else uc -= s3;
-            if (!found) {
-                for (int k = 0; k < S.np1d; ++k) {
-                    const float e = sm.e1[k * S.nz + izn];
-                    if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
-                    uc -= e;
+                ++n_coll;
+                // implicit capture
+                const float wn = p.w * omg;
+                if (wn < p.w) {
+                    w_atm += double(p.w) - double(wn);
+                    if (want_heat) {
+                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                        tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
+                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
+                        ++n_tally;
+                    }
                 }
-            }
-            ++n_coll;
-            fac = omg;
-        } else {
-            // ---- surface hit
-            ++n_sfc;
-            u = rng4(g);
-            int sx, sy;
-            if (p.frozen) {
-                sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
-                sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
+                p.w = wn;
+                p.order++; p.direct = false;
+                if (!(p.w > 0.0f)) { alive = false; continue; }
+                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                    if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
+                    else { p.cix = fx; p.ciy = fy; }
+                    p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                    p.frozen = true;
+                }
             } else {
-                sx = min(S.sfc_nx - 1, max(0, int(p.x * S.inv_Lx * float(S.sfc_nx))));
-                sy = min(S.sfc_ny - 1, max(0, int(p.y * S.inv_Ly * float(S.sfc_ny))));
-            }
-            const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
-            sfc_type = __ldg(S.sfc_type + si);
-#pragma unroll
-            for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
-            if (want_rad && S.nz3 > 0 && S.iz0 == 0) {
-                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
-            }
-            fac = 1.0f;
-        }
-
-        // ---- weight after the interaction (collision: implicit capture) and book-keeping
-        if (ev == EV_COLL) {
-            const float wn = p.w * fac;
-            if (wn < p.w) {
-                w_atm += double(p.w) - double(wn);
-                if (want_heat) {
-                    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                    tally_add(S.heat + (size_t(J.slab) * S.nz + p.iz) * nxy + size_t(hy) * S.nx + hx,
-                              (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + p.iz) : 1.0));
-                    ++n_tally;
-                }
-            }
-            p.w = wn;
-            p.order++; p.direct = false;
-            if (!(p.w > 0.0f)) { alive = false; continue; }
-            if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
-                if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
-                else { p.cix = fx; p.ciy = fy; }
-                p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                p.frozen = true;
-            }
-        }
-
-        // ---- local estimates toward every sensor (shared by both event kinds)
-        if (want_rad) {
-            for (int k = 0; k < S.nrad; ++k) {
-                const DevSensor& se = S.sens[k];
-                const float dzs = (se.zt - p.z) * se.s.z;
-                if (!(dzs > 0.0f)) continue;
-                float f;
-                if (ev == EV_COLL) {
-                    const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
-                    f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
+                // ---- surface hit
+                ++n_sfc;
+                u = rng4(g);
+                int sx, sy;
+                if (p.frozen) {
+                    sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
+                    sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
                 } else {
-                    f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm, wi, se.s) * se.s.z : 0.0f;
+                    sx = min(S.sfc_nx - 1, max(0, int(p.x * S.inv_Lx * float(S.sfc_nx))));
+                    sy = min(S.sfc_ny - 1, max(0, int(p.y * S.inv_Ly * float(S.sfc_ny))));
                 }
-                if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
+                const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
+                sfc_type = __ldg(S.sfc_type + si);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
+                if (want_rad && S.nz3 > 0 && S.iz0 == 0) {
+                    fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                    fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
+                }
             }
-        }
 
-        // ---- new direction
-        if (ev == EV_COLL) {
-            float xi_tab = 0.5f;
-            if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
-            const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
-            newd = rotate_dir(p.d, mu, RT_2PI * u.w);
-            if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
-        } else {
-            float3 wo = make_float3(0.f, 0.f, 1.f);
-            fac = 0.0f;
-            bool diffuse = true;
-            if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
-            if (diffuse) {
-                const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
-                float sp, cp;
-                __sincosf(RT_2PI * u.y, &sp, &cp);
-                wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
-                fac = (sfc_type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
-            } else {
-                const float sig2 = fmaxf(1e-6f, prm[4]);
-                const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
-                float sp, cp;
-                __sincosf(RT_2PI * u.y, &sp, &cp);
-                const float zx = r * cp, zy = r * sp;
-                const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
-                const float3 n = make_float3(-zx * nn, -zy * nn, nn);
-                const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
-                if (cosg > 0.0f) {
-                    wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
-                    if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
+            // ---- local estimates toward every sensor (shared by both event kinds)
+            if (want_rad) {
+                for (int k = 0; k < S.nrad; ++k) {
+                    const DevSensor& se = S.sens[k];
+                    const float dzs = (se.zt - p.z) * se.s.z;
+                    if (!(dzs > 0.0f)) continue;
+                    float f;
+                    if (evk == EV_COLL) {
+                        const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
+                        f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
+                    } else {
+                        f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm, wi, se.s) * se.s.z : 0.0f;
+                    }
+                    if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
                 }
             }
-            const float wn = p.w * fac;
-            w_sfc += double(p.w) - double(wn);
-            p.w = wn;
-            if (!(p.w > 0.0f)) { alive = false; continue; }
-            const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
-            newd = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
-            p.direct = false; p.order++;
-        }
-        p.d = newd;
-        invd = inv_dir(p.d);
-        if (ev == EV_SFC) {
-            if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
-            if (S.nz3 > 0 && S.iz0 == 0 && !p.frozen) {
-                p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
-                p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+
+            // ---- new direction
+            if (evk == EV_COLL) {
+                float xi_tab = 0.5f;
+                if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
+                const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
+                newd = rotate_dir(p.d, mu, RT_2PI * u.w);
+                if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
+            } else {
+                float3 wo = make_float3(0.f, 0.f, 1.f);
+                float fac = 0.0f;
+                bool diffuse = true;
+                if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
+                if (diffuse) {
+                    const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
+                    float sp, cp;
+                    __sincosf(RT_2PI * u.y, &sp, &cp);
+                    wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
+                    fac = (sfc_type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
+                } else {
+                    const float sig2 = fmaxf(1e-6f, prm[4]);
+                    const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
+                    float sp, cp;
+                    __sincosf(RT_2PI * u.y, &sp, &cp);
+                    const float zx = r * cp, zy = r * sp;
+                    const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
+                    const float3 n = make_float3(-zx * nn, -zy * nn, nn);
+                    const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
+                    if (cosg > 0.0f) {
+                        wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
+                        if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
+                    }
+                }
+                const float wn = p.w * fac;
+                w_sfc += double(p.w) - double(wn);
+                p.w = wn;
+                if (!(p.w > 0.0f)) { alive = false; continue; }
+                const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
+                newd = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
+                p.direct = false; p.order++;
             }
-            if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
-                p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                p.frozen = true;
+            p.d = newd;
+            invd = inv_dir(p.d);
+            if (evk == EV_SFC) {
+                if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
+                if (S.nz3 > 0 && S.iz0 == 0 && !p.frozen) {
+                    p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                    p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+                }
+                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                    p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                    p.frozen = true;
+                }
             }
+            // ---- Russian roulette (Pho_wmin / Pho_wfac), shared
+            if (p.w < S.wmin) {
+                float xi = u.w;
+                if (evk == EV_COLL) { const float4 v = rng4(g); xi = v.x; }
+                if (xi * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
+                else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
+            }
+            if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
         }
-        // ---- Russian roulette (Pho_wmin / Pho_wfac), shared
-        if (p.w < S.wmin) {
-            float xi = u.w;
-            if (ev == EV_COLL) { const float4 v = rng4(g); xi = v.x; }
-            if (xi * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
-            else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
-        }
-        if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
     }
 
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
@@ -809,16 +840,16 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
         unsigned long long v = c[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
         c[i] = v;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double v = dsum[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
         dsum[i] = v;
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         unsigned long long* sc = reinterpret_cast<unsigned long long*>(S.stats);
         for (int i = 0; i < 9; ++i) if (c[i]) atomicAdd(sc + i, c[i]);
         atomicAdd(&S.stats->w_toa, dsum[0]); atomicAdd(&S.stats->w_sfc, dsum[1]);
@@ -1039,7 +1070,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     int shx = log2floor(std::max(1, opt->cmx > 0 ? opt->cmx : 4)), shy = log2floor(std::max(1, opt->cmy > 0 ? opt->cmy : 4));
     int cmz = opt->cmz > 0 ? opt->cmz : 8;
     if (per_level) { shx = 0; shy = 0; cmz = 1; }
-    S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 3;
+    S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 16;
+    S.event_min = opt->event_min > 0 ? opt->event_min : 16;
+    S.regen_min = opt->regen_min > 0 ? opt->regen_min : 8;
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;

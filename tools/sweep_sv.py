@@ -16,11 +16,14 @@ for cfg in configs:
     sv = cfg[:3]
     cm = cfg[3:6] if len(cfg) >= 6 else (0, 0, 0)
     K = cfg[6] if len(cfg) > 6 else 0
-    tpb = cfg[7] if len(cfg) > 7 else 0
-    bps = cfg[8] if len(cfg) > 8 else 0
+    E = cfg[7] if len(cfg) > 7 else 0
+    R = cfg[8] if len(cfg) > 8 else 0
+    tpb = cfg[9] if len(cfg) > 9 else 0
+    bps = cfg[10] if len(cfg) > 10 else 0
     m = mcarats_ng(**dict(kw, dry_run=True, supervoxel=sv))
     m.options.cmx, m.options.cmy, m.options.cmz = cm
     m.options.flight_steps = K
+    m.options.event_min, m.options.regen_min = E, R
     m.options.threads_per_block = tpb
     m.options.blocks_per_sm = bps
     jobs, keep = abi.make_jobs(**m.jobs_args)
@@ -28,6 +31,6 @@ for cfg in configs:
     sol.run(jobs); sol.run(jobs)
     st = sol.stats()
     n = st['photons']
-    print('sv=%s cm=%s K=%d tpb=%d bps=%d : %.1f Mph/s | per photon: cell %.1f tent %.1f coll %.1f sfc %.2f le %.1f visit %.1f | bytes/ph %.0f' % (
-        sv, cm, K, tpb, bps, n / st['elapsed_ms'] / 1e3, st['n_cell'] / n, st['n_tent'] / n, st['n_coll'] / n, st['n_sfc'] / n, st['n_le'] / n,
+    print('sv=%s cm=%s K=%d E=%d R=%d tpb=%d bps=%d : %.1f Mph/s | per photon: cell %.1f tent %.1f coll %.1f sfc %.2f le %.1f visit %.1f | bytes/ph %.0f' % (
+        sv, cm, K, E, R, tpb, bps, n / st['elapsed_ms'] / 1e3, st['n_cell'] / n, st['n_tent'] / n, st['n_coll'] / n, st['n_sfc'] / n, st['n_le'] / n,
         st['n_le_visit'] / n, st['bytes_alg'] / n), flush=True)
