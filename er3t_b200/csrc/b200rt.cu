@@ -224,8 +224,8 @@ __device__ __forceinline__ float wrapf(float x, float L, float invL) {
 
 __device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
 
-__device__ __forceinline__ void flux_tally(const DevScene& S, const DevJob& J, const Photon& p, int var, int lev,
-                                           unsigned& n_tally) {
+__device__ __noinline__ void flux_tally(const DevScene& S, const DevJob& J, const Photon& p, int var, int lev,
+                                       unsigned& n_tally) {
     int fx, fy;
     if (p.frozen) { fx = p.cix; fy = p.ciy; }
     else {
@@ -260,32 +260,13 @@ __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int 
     return fabsf(c2 - ca) * inv_absdz;
 }
 
-// Optical depth (extinction + gas absorption) from (x,y,z) along sensor direction to the sensor's target level.
-// fx, fy: fine column if the start point lies in a 3-D layer (else recomputed); s3: 3-D extinction of the start voxel.
-__device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs, int fx, int fy,
-                        float s3, unsigned& n_visit) {
+// exact traversal toward a sensor: layer by layer, column by column inside the 3-D block (oblique views, sensors
+// inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.
+__device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs,
+                                             int fx, int fy, bool in3, unsigned& n_visit) {
     const float* ab = S.job_abs + size_t(p.job) * S.nz;
-    const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
     const int iz = p.iz;
     const size_t nxy = size_t(S.nx) * S.ny;
-    const bool in3 = (S.nz3 > 0) && iz >= S.iz0 && iz < S.iz0 + S.nz3;
-    if (se.fast_ok && se.s.z > 0.0f && (p.frozen || se.vertical_up)) {
-        // ---- vertical (or column-frozen) fast path: O(1) look-ups in the precomputed tables
-        float t1 = (sm.e1cum[se.lt] + sm.e1tot[se.lt] * (se.zt - sm.z[se.lt])) - (sm.e1cum[iz] + sm.e1tot[iz] * (p.z - sm.z[iz]));
-        if (has_abs) t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
-        if (S.nz3 > 0 && iz < S.iz0 + S.nz3) {
-            if (!in3) {
-                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                t1 += __ldg(S.tu3 + size_t(fy) * S.nx + fx);
-            } else {
-                t1 += __ldg(S.tu3 + size_t(iz - S.iz0 + 1) * nxy + size_t(fy) * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
-            }
-            ++n_visit;
-        }
-        return fmaxf(0.0f, t1) * se.inv_sz;
-    }
-    // ---- generic path: exact traversal, layer by layer, column by column inside the 3-D block
     float tau = 0.0f;
     float x = p.x, y = p.y, z = p.z;
     int l = iz;
@@ -343,6 +324,34 @@ __device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, 
     return tau;
 }
 
+// Optical depth (extinction + gas absorption) from (x,y,z) along sensor direction to the sensor's target level.
+// fx, fy: fine column if the start point lies in a 3-D layer (else recomputed); s3: 3-D extinction of the start voxel.
+__device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs, int fx, int fy,
+                        float s3, unsigned& n_visit) {
+    const float* ab = S.job_abs + size_t(p.job) * S.nz;
+    const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
+    const int iz = p.iz;
+    const size_t nxy = size_t(S.nx) * S.ny;
+    const bool in3 = (S.nz3 > 0) && iz >= S.iz0 && iz < S.iz0 + S.nz3;
+    if (se.fast_ok && se.s.z > 0.0f && (p.frozen || se.vertical_up)) {
+        // ---- vertical (or column-frozen) fast path: O(1) look-ups in the precomputed tables
+        float t1 = (sm.e1cum[se.lt] + sm.e1tot[se.lt] * (se.zt - sm.z[se.lt])) - (sm.e1cum[iz] + sm.e1tot[iz] * (p.z - sm.z[iz]));
+        if (has_abs) t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
+        if (S.nz3 > 0 && iz < S.iz0 + S.nz3) {
+            if (!in3) {
+                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                t1 += __ldg(S.tu3 + size_t(fy) * S.nx + fx);
+            } else {
+                t1 += __ldg(S.tu3 + size_t(iz - S.iz0 + 1) * nxy + size_t(fy) * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
+            }
+            ++n_visit;
+        }
+        return fmaxf(0.0f, t1) * se.inv_sz;
+    }
+    return le_tau_generic(S, sm, se, p, has_abs, fx, fy, in3, n_visit);
+}
+
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
 __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevJob& J, const DevSensor& se,
                                            const Photon& p, float fw, int fx, int fy, float s3, unsigned& n_le,
@@ -367,6 +376,37 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
 
 __device__ __forceinline__ float3 inv_dir(const float3 d) {
     return make_float3(d.x != 0.0f ? 1.0f / d.x : RT_INF, d.y != 0.0f ? 1.0f / d.y : RT_INF, d.z != 0.0f ? 1.0f / d.z : RT_INF);
+}
+
+// sample the reflected direction `wo` at a surface of the given type; returns the weight factor (BRDF cos / pdf)
+__device__ __noinline__ float surface_sample(int sfc_type, const float* prm, const float3 wi, const float4 u, float3& wo) {
+    wo = make_float3(0.f, 0.f, 1.f);
+    float fac = 0.0f;
+    bool diffuse = true;
+    if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
+    if (diffuse) {
+        // cosine-weighted direction: Lambertian (type 1), whitecap part of DSM, LSRT with weight = pi * f_r
+        const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
+        float sp, cp;
+        __sincosf(RT_2PI * u.y, &sp, &cp);
+        wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
+        fac = (sfc_type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
+    } else {
+        // Cox-Munk facet: slope from the isotropic Gaussian, mirror reflection, weight F cos(gamma) / (mu_i mu_n) S
+        const float sig2 = fmaxf(1e-6f, prm[4]);
+        const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
+        float sp, cp;
+        __sincosf(RT_2PI * u.y, &sp, &cp);
+        const float zx = r * cp, zy = r * sp;
+        const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
+        const float3 n = make_float3(-zx * nn, -zy * nn, nn);
+        const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
+        if (cosg > 0.0f) {
+            wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
+            if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
+        }
+    }
+    return fac;
 }
 
 // Persistent-thread photon transport.  Every thread owns one photon at a time and regenerates it in place from a
@@ -776,30 +816,8 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                 newd = rotate_dir(p.d, mu, RT_2PI * u.w);
                 if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
             } else {
-                float3 wo = make_float3(0.f, 0.f, 1.f);
-                float fac = 0.0f;
-                bool diffuse = true;
-                if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
-                if (diffuse) {
-                    const float ct = sqrtf(u.x), st = sqrtf(1.0f - u.x);
-                    float sp, cp;
-                    __sincosf(RT_2PI * u.y, &sp, &cp);
-                    wo = make_float3(st * cp, st * sp, fmaxf(ct, 1e-6f));
-                    fac = (sfc_type == B200RT_SFC_LSRT) ? lsrt_kernel_sum(prm, wi, wo) : prm[0];
-                } else {
-                    const float sig2 = fmaxf(1e-6f, prm[4]);
-                    const float r = sqrtf(-sig2 * __logf(1.0f - u.x * 0.99999994f));
-                    float sp, cp;
-                    __sincosf(RT_2PI * u.y, &sp, &cp);
-                    const float zx = r * cp, zy = r * sp;
-                    const float nn = rsqrtf(1.0f + zx * zx + zy * zy);
-                    const float3 n = make_float3(-zx * nn, -zy * nn, nn);
-                    const float cosg = wi.x * n.x + wi.y * n.y + wi.z * n.z;
-                    if (cosg > 0.0f) {
-                        wo = make_float3(2.0f * cosg * n.x - wi.x, 2.0f * cosg * n.y - wi.y, 2.0f * cosg * n.z - wi.z);
-                        if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
-                    }
-                }
+                float3 wo;
+                const float fac = surface_sample(sfc_type, prm, wi, u, wo);
                 const float wn = p.w * fac;
                 w_sfc += double(p.w) - double(wn);
                 p.w = wn;

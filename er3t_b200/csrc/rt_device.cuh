@@ -92,7 +92,7 @@ __device__ __forceinline__ float ray_sample(float xi) {
     return fminf(1.0f, fmaxf(-1.0f, q - 1.0f / q));
 }
 
-__device__ __forceinline__ float tab_eval1(const PhaseTab& T, int it, float mu) {
+__device__ __noinline__ float tab_eval1(const PhaseTab& T, int it, float mu) {
     const float* m = T.mu;
     const int n = T.nang;
     if (mu >= __ldg(m)) return __ldg(T.p + size_t(it) * n);
@@ -108,7 +108,7 @@ __device__ __forceinline__ float tab_eval1(const PhaseTab& T, int it, float mu) 
     return p0 + f * (p1 - p0);
 }
 
-__device__ __forceinline__ float tab_sample1(const PhaseTab& T, int it, float xi) {
+__device__ __noinline__ float tab_sample1(const PhaseTab& T, int it, float xi) {
     const int n = T.nang;
     const float* F = T.cdf + size_t(it) * n;
     int lo = 0, hi = n - 1;                 // F[lo] <= xi < F[hi]
@@ -221,7 +221,7 @@ __device__ __forceinline__ float lsrt_kernel_sum(const float* p, const float3 wi
     const float v = p[0] + p[1] * kgeo + p[2] * kvol;
     return v > 0.0f ? v : 0.0f;
 }
-__device__ __forceinline__ float brdf_eval(int type, const float* p, const float3 wi, const float3 wo) {
+__device__ __noinline__ float brdf_eval(int type, const float* p, const float3 wi, const float3 wo) {
     if (wi.z <= 0.0f || wo.z <= 0.0f) return 0.0f;
     if (type == 2) return p[1] * p[0] * (1.0f / RT_PI) + (1.0f - p[1]) * dsm_spec_brdf(p, wi, wo);
     if (type == 4) return lsrt_kernel_sum(p, wi, wo) * (1.0f / RT_PI);
