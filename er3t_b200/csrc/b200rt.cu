@@ -34,6 +34,7 @@ struct DevSensor {
     int vertical_up;     // s == (0,0,1): precomputed tau-to-top table applies in 3-D mode
     int fast_ok;         // zt is at/above the top of the 3-D block
     long long off;       // offset of this sensor inside a radiance slab
+    double npix;         // nxr * nyr
 };
 
 struct DevJob {
@@ -41,7 +42,7 @@ struct DevJob {
     unsigned long long count;   // photons of this job handled by this GPU
     unsigned long long seed;
     double norm;                // mu0 * src_flx / nphot(job, all GPUs)
-    double rad_scale;
+    double rad_fac;             // norm * rad_scale
     int slab;
     int has_abs;
     int has_fscale;
@@ -188,14 +189,18 @@ struct Smem {
     const float* e1;      // [np1d][nz]
     const float* o1;
     const float* a1;
-    const float* maj1d;   // [nslab_z]   majorant of the 1-D part of a fine z slab
-    const int* lay0;      // [nslab_z+1] first layer of each fine z slab
-    const int* cz;        // [nslab_z]   fine z index in the majorant grid, -1 for 1-D slabs
-    const int* cg;        // [nslab_z]   coarse group of each fine slab
-    const float* g_maj1d; // [ngroup]    majorant of the 1-D part of a coarse group
-    const int* g_lo;      // [ngroup+1]  first fine slab of each coarse group
-    const int* g_cz;      // [ngroup]    coarse z index in the emptiness grid, -1 for pure 1-D groups
+    // packed per-cell records: one 16-byte shared-memory load each instead of a chain of dependent look-ups
+    const float4* slabA;  // [nslab_z]   (zlo, zhi, 1-D majorant, bits: fine z index in the majorant grid or -1)
+    const int4* slabB;    // [nslab_z]   (first layer, one-past-last layer, coarse group, -)
+    const float4* grpA;   // [ngroup]    (zlo, zhi, 1-D majorant, bits: coarse z index in the emptiness grid or -1)
+    const int4* grpB;     // [ngroup]    (first fine slab, one-past-last fine slab, first layer, one-past-last layer)
+    double* acc;          // per-thread energy accumulators [4][blockDim]: toa, sfc, atm, roulette
+    unsigned* cnt;        // per-thread event counters [8][blockDim]
 };
+enum { ACC_TOA = 0, ACC_SFC = 1, ACC_ATM = 2, ACC_RR = 3 };
+enum { CNT_PHOT = 0, CNT_TENT = 1, CNT_COLL = 2, CNT_SFC = 3, CNT_LE = 4, CNT_VISIT = 5, CNT_TALLY = 6, CNT_KILL = 7 };
+#define ACC(k) sm.acc[(k) * blockDim.x + threadIdx.x]
+#define CNT(k) sm.cnt[(k) * blockDim.x + threadIdx.x]
 
 struct Photon {
     float x, y, z;
@@ -207,6 +212,7 @@ struct Photon {
     int iz;           // layer of the last event / crossing
     int order;
     int job;
+    int jflags;       // bit 0: job has gas absorption, bit 1: job has per-level scale factors
     float za;         // start of the current straight leg (for path-integrated gas absorption)
     int iza;
     float leg;        // length of the current leg
@@ -224,19 +230,30 @@ __device__ __forceinline__ float wrapf(float x, float L, float invL) {
 
 __device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
 
-__device__ __noinline__ void flux_tally(const DevScene& S, const DevJob& J, const Photon& p, int var, int lev,
-                                       unsigned& n_tally) {
+__device__ __noinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
     int fx, fy;
     if (p.frozen) { fx = p.cix; fy = p.ciy; }
     else {
         fx = min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
         fy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
     }
+    const DevJob& J = S.jobs[p.job];
     const size_t nxy = size_t(S.nx) * S.ny;
     double sc = J.norm * double(nxy);
-    if (J.has_fscale) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + lev);
+    if (p.jflags & 2) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + lev);
     tally_add(S.flux + ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx, double(p.w) * sc);
-    ++n_tally;
+    CNT(CNT_TALLY)++;
+}
+
+__device__ __noinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
+    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+    const DevJob& J = S.jobs[p.job];
+    const size_t nxy = size_t(S.nx) * S.ny;
+    double sc = J.norm * double(nxy);
+    if (p.jflags & 2) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + iz);
+    tally_add(S.heat + (size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx, dep * sc);
+    CNT(CNT_TALLY)++;
 }
 
 // layer that contains z among layers [l0, l1)
@@ -262,11 +279,13 @@ __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int 
 
 // exact traversal toward a sensor: layer by layer, column by column inside the 3-D block (oblique views, sensors
 // inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.
-__device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs,
-                                             int fx, int fy, bool in3, unsigned& n_visit) {
+__device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p,
+                                             int fx, int fy, bool in3) {
+    const int has_abs = p.jflags & 1;
     const float* ab = S.job_abs + size_t(p.job) * S.nz;
     const int iz = p.iz;
-    const size_t nxy = size_t(S.nx) * S.ny;
+    const int nxy = S.nx * S.ny;
+    unsigned n_visit = 0;
     float tau = 0.0f;
     float x = p.x, y = p.y, z = p.z;
     int l = iz;
@@ -288,7 +307,7 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, 
             if (!p.frozen) { x = wrapf(x + se.s.x * dl, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * dl, S.Ly, S.inv_Ly); }
             have_col = p.frozen;
         } else if (p.frozen) {
-            tau += (base + __ldg(S.ext3tot + size_t(l - S.iz0) * nxy + size_t(fy) * S.nx + fx)) * dl;
+            tau += (base + __ldg(S.ext3tot + (l - S.iz0) * nxy + fy * S.nx + fx)) * dl;
             ++n_visit;
         } else {
             if (!have_col) {
@@ -303,7 +322,7 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, 
                 if (se.s.y > 0.0f) ty = (float(fy + 1) * S.dy - y) * isy; else if (se.s.y < 0.0f) ty = (float(fy) * S.dy - y) * isy;
                 tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
                 const float step = fminf(rem, fminf(tx, ty));
-                tau += (base + __ldg(S.ext3tot + size_t(l - S.iz0) * nxy + size_t(fy) * S.nx + fx)) * step;
+                tau += (base + __ldg(S.ext3tot + (l - S.iz0) * nxy + fy * S.nx + fx)) * step;
                 ++n_visit;
                 if (step >= rem) { x += se.s.x * rem; y += se.s.y * rem; break; }
                 rem -= step;
@@ -321,43 +340,45 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, 
         if (up) { if (zb >= se.zt || l + 1 >= S.nz) break; l++; }
         else { if (zb <= se.zt || l == 0) break; l--; }
     }
+    CNT(CNT_VISIT) += n_visit;
     return tau;
 }
 
-// Optical depth (extinction + gas absorption) from (x,y,z) along sensor direction to the sensor's target level.
-// fx, fy: fine column if the start point lies in a 3-D layer (else recomputed); s3: 3-D extinction of the start voxel.
-__device__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int has_abs, int fx, int fy,
-                        float s3, unsigned& n_visit) {
-    const float* ab = S.job_abs + size_t(p.job) * S.nz;
-    const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
+// Optical depth (extinction + gas absorption) from the photon position along the sensor direction to the sensor's
+// target level.  fx, fy: fine column if the start point lies in a 3-D layer (else recomputed); s3: 3-D extinction of
+// the start voxel.
+__device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int fx, int fy,
+                                        float s3) {
     const int iz = p.iz;
-    const size_t nxy = size_t(S.nx) * S.ny;
     const bool in3 = (S.nz3 > 0) && iz >= S.iz0 && iz < S.iz0 + S.nz3;
     if (se.fast_ok && se.s.z > 0.0f && (p.frozen || se.vertical_up)) {
         // ---- vertical (or column-frozen) fast path: O(1) look-ups in the precomputed tables
         float t1 = (sm.e1cum[se.lt] + sm.e1tot[se.lt] * (se.zt - sm.z[se.lt])) - (sm.e1cum[iz] + sm.e1tot[iz] * (p.z - sm.z[iz]));
-        if (has_abs) t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
+        if (p.jflags & 1) {
+            const float* ab = S.job_abs + size_t(p.job) * S.nz;
+            const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
+            t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
+        }
         if (S.nz3 > 0 && iz < S.iz0 + S.nz3) {
+            const int nxy = S.nx * S.ny;
             if (!in3) {
                 fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
                 fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                t1 += __ldg(S.tu3 + size_t(fy) * S.nx + fx);
+                t1 += __ldg(S.tu3 + fy * S.nx + fx);
             } else {
-                t1 += __ldg(S.tu3 + size_t(iz - S.iz0 + 1) * nxy + size_t(fy) * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
+                t1 += __ldg(S.tu3 + (iz - S.iz0 + 1) * nxy + fy * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
             }
-            ++n_visit;
+            CNT(CNT_VISIT)++;
         }
         return fmaxf(0.0f, t1) * se.inv_sz;
     }
-    return le_tau_generic(S, sm, se, p, has_abs, fx, fy, in3, n_visit);
+    return le_tau_generic(S, sm, se, p, fx, fy, in3);
 }
 
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
-__device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevJob& J, const DevSensor& se,
-                                           const Photon& p, float fw, int fx, int fy, float s3, unsigned& n_le,
-                                           unsigned& n_visit, unsigned& n_tally) {
-    const float tau = le_tau(S, sm, se, p, J.has_abs, fx, fy, s3, n_visit);
-    ++n_le;
+__device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, float fw,
+                                           int fx, int fy, float s3) {
+    const float tau = le_tau(S, sm, se, p, fx, fy, s3);
     const float contrib = fw * __expf(-tau) * se.inv_sz;
     int px, py;
     if (p.frozen) {
@@ -369,9 +390,10 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
         px = min(se.nxr - 1, max(0, int(xr * S.inv_Lx * float(se.nxr))));
         py = min(se.nyr - 1, max(0, int(yr * S.inv_Ly * float(se.nyr))));
     }
-    tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + size_t(py) * se.nxr + px,
-              double(contrib) * J.norm * J.rad_scale * double(se.nxr) * double(se.nyr));
-    ++n_tally;
+    const DevJob& J = S.jobs[p.job];
+    tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
+    CNT(CNT_LE)++;
+    CNT(CNT_TALLY)++;
 }
 
 __device__ __forceinline__ float3 inv_dir(const float3 d) {
@@ -417,63 +439,73 @@ __device__ __noinline__ float surface_sample(int sfc_type, const float* prm, con
 //                         tentative collision / the surface / TOA park, the loop ends when >= event_min lanes are parked,
 //   (3) tentative phase   Philox draw + voxel extinction look-up + null-collision rejection for all parked lanes,
 //   (4) event phase       shared by real collisions and surface hits: local estimates, new direction, roulette.
-__global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant__ DevScene S) {
-    extern __shared__ float smem_f[];
+// PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
+// FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
+template <bool PL, bool FZ>
+__global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant__ DevScene S) {
+    extern __shared__ float4 smem_f4[];
     Smem sm;
     {
-        float* q = smem_f;
+        // 16-byte records first, then the double accumulators, then 4-byte tables
+        float4* q4 = smem_f4;
+        float4* slabA = q4; q4 += S.nslab_z;
+        int4* slabB = reinterpret_cast<int4*>(q4); q4 += S.nslab_z;
+        float4* grpA = q4; q4 += S.ngroup;
+        int4* grpB = reinterpret_cast<int4*>(q4); q4 += S.ngroup;
+        double* acc = reinterpret_cast<double*>(q4);
+        unsigned* cnt = reinterpret_cast<unsigned*>(acc + 4 * blockDim.x);
+        float* q = reinterpret_cast<float*>(cnt + 8 * blockDim.x);
         float* z = q; q += S.nz + 1;
         float* e1tot = q; q += S.nz;
         float* e1cum = q; q += S.nz + 1;
         float* e1 = q; q += S.np1d * S.nz;
         float* o1 = q; q += S.np1d * S.nz;
         float* a1 = q; q += S.np1d * S.nz;
-        float* maj1d = q; q += S.nslab_z;
-        float* g_maj1d = q; q += S.ngroup;
-        int* lay0 = reinterpret_cast<int*>(q); q += S.nslab_z + 1;
-        int* cz = reinterpret_cast<int*>(q); q += S.nslab_z;
-        int* cg = reinterpret_cast<int*>(q); q += S.nslab_z;
-        int* g_lo = reinterpret_cast<int*>(q); q += S.ngroup + 1;
-        int* g_cz = reinterpret_cast<int*>(q);
         for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
         for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
-        for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) { maj1d[i] = S.slab_maj1d[i]; cz[i] = S.slab_cz[i]; cg[i] = S.slab_cg[i]; }
-        for (int i = threadIdx.x; i <= S.nslab_z; i += blockDim.x) lay0[i] = S.slab_lay0[i];
-        for (int i = threadIdx.x; i < S.ngroup; i += blockDim.x) { g_maj1d[i] = S.group_maj1d[i]; g_cz[i] = S.group_cz[i]; }
-        for (int i = threadIdx.x; i <= S.ngroup; i += blockDim.x) g_lo[i] = S.group_lo[i];
+        for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) {
+            const int l0 = S.slab_lay0[i], l1 = S.slab_lay0[i + 1];
+            slabA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.slab_maj1d[i], __int_as_float(S.slab_cz[i]));
+            slabB[i] = make_int4(l0, l1, S.slab_cg[i], 0);
+        }
+        for (int i = threadIdx.x; i < S.ngroup; i += blockDim.x) {
+            const int s0 = S.group_lo[i], s1 = S.group_lo[i + 1];
+            const int l0 = S.slab_lay0[s0], l1 = S.slab_lay0[s1];
+            grpA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.group_maj1d[i], __int_as_float(S.group_cz[i]));
+            grpB[i] = make_int4(s0, s1, l0, l1);
+        }
+        for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
+        for (int k = 0; k < 8; ++k) cnt[k * blockDim.x + threadIdx.x] = 0u;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
-        sm.maj1d = maj1d; sm.lay0 = lay0; sm.cz = cz; sm.cg = cg; sm.g_maj1d = g_maj1d; sm.g_lo = g_lo; sm.g_cz = g_cz;
+        sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.cnt = cnt;
     }
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const bool want_flux = (S.target & B200RT_TARGET_FLUX) != 0;
+    const bool want_flux = PL && (S.target & B200RT_TARGET_FLUX) != 0;
     const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
-    const bool want_heat = (S.target & B200RT_TARGET_HEATING) != 0;
-    const bool per_level = want_flux || want_heat;       // every z crossing is a level crossing (svz = 1, no groups)
-    const size_t nxy = size_t(S.nx) * S.ny;
+    const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
+    const int nxy = S.nx * S.ny;
 
-    unsigned n_cell = 0, n_tent = 0, n_coll = 0, n_sfc = 0, n_le = 0, n_visit = 0, n_tally = 0, n_kill = 0, n_phot = 0;
-    double w_toa = 0.0, w_sfc = 0.0, w_atm = 0.0, w_rr = 0.0;
-
+    unsigned n_cell = 0;
     Photon p;
-    Philox4 g;
-    DevJob J;
+    uint32_t rc0 = 0, rc1 = 0, rc2 = 0;   // Philox counter: photon index (lo, hi) and draw number
     float3 invd = make_float3(0.f, 0.f, 0.f);
     bool alive = false;
     bool exhausted = false;
     bool stale = false;          // p.is may not be the fine slab of p.z (after sideways moves in empty coarse cells)
     int ev = EV_NONE;
-    p.job = -1;
-    g.c3 = 0xB200u;
-    // hand-off from the flight loop to the tentative / event phases
-    float ev_M = 0.0f, ev_s3 = 0.0f, ev_uc = 0.0f;
-    float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
-    int ev_fx = 0, ev_fy = 0;
-    size_t ev_vox = 0;
-    bool ev_in3 = false, ev_empty = false;
+    p.job = 0; p.jflags = 0; p.frozen = false;
+
+#define RNG4(out)                                                                                              \
+    {                                                                                                          \
+        const unsigned long long seed_ = S.jobs[p.job].seed;                                                   \
+        const uint4 r_ = philox4x32_10(rc0, rc1, rc2, 0xB200u, unsigned(seed_), unsigned(seed_ >> 32));        \
+        rc2++;                                                                                                 \
+        out = make_float4(u01(r_.x), u01(r_.y), u01(r_.z), u01(r_.w));                                          \
+    }
 
     for (;;) {
         // =========================================================== (1) regeneration (batched)
@@ -495,27 +527,29 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                             const int mid = (lo + hi + 1) >> 1;
                             if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
                         }
-                        if (lo != p.job) { J = S.jobs[lo]; p.job = lo; }
+                        p.job = lo;
+                        const DevJob& J = S.jobs[lo];
+                        p.jflags = J.has_abs | (J.has_fscale << 1);
                         const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
-                        g.k0 = unsigned(J.seed); g.k1 = unsigned(J.seed >> 32);
-                        g.c0 = unsigned(gidx); g.c1 = unsigned(gidx >> 32); g.c2 = 0;
-                        const float4 u = rng4(g);
-                        const float4 v = rng4(g);
+                        rc0 = unsigned(gidx); rc1 = unsigned(gidx >> 32); rc2 = 0;
+                        float4 u, v;
+                        RNG4(u);
+                        RNG4(v);
                         p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
                         if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
                         else p.d = S.src;
                         p.w = 1.0f; p.order = 0; p.direct = true;
                         p.is = S.nslab_z - 1; p.iz = S.nz - 1;
                         p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
-                        p.frozen = (S.solver == B200RT_SOLVER_IPA);
+                        p.frozen = FZ && (S.solver == B200RT_SOLVER_IPA);
                         p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
                         p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
-                        if (p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
+                        if (FZ && p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
                         p.tau = -__logf(v.x);
                         invd = inv_dir(p.d);
                         alive = true; stale = false; ev = EV_NONE;
-                        ++n_phot;
-                        if (want_flux) { flux_tally(S, J, p, 0, S.nz, n_tally); flux_tally(S, J, p, 1, S.nz, n_tally); }
+                        CNT(CNT_PHOT)++;
+                        if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
                     }
                 }
             }
@@ -523,45 +557,56 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
         }
 
         // =========================================================== (2) flight: geometry only
+        float ev_M = 0.0f;
+        bool ev_in3 = false, ev_empty = false;
 #pragma unroll 1
         for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
             if (alive && ev == EV_NONE) {
                 int is = p.is;
-                const int grp = sm.cg[is];
-                const int gcz = sm.g_cz[grp];
+                int4 sb = sm.slabB[is];                     // l0, l1, group
+                const int grp = sb.z;
+                const float4 ga = sm.grpA[grp];             // zlo, zhi, maj1d, gcz
+                const int gcz = __float_as_int(ga.w);
                 const bool in3 = gcz >= 0;
                 bool empty = !in3;
                 if (in3) {
-                    empty = __ldg(S.empty3 + (size_t(gcz) * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
+                    empty = __ldg(S.empty3 + (gcz * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
                     ++n_cell;
                 }
-                if (!empty && stale) {
+                if (!PL && !empty && stale) {
                     // entered a non-empty coarse cell sideways: find the fine z slab of the current height
-                    int lo = sm.g_lo[grp], hi = sm.g_lo[grp + 1] - 1;
+                    const int4 gb = sm.grpB[grp];
+                    int lo = gb.x, hi = gb.y - 1;
                     while (lo < hi) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if (p.z >= sm.z[sm.lay0[mid]]) lo = mid; else hi = mid - 1;
+                        if (p.z >= sm.slabA[mid].x) lo = mid; else hi = mid - 1;
                     }
                     is = lo; p.is = lo;
+                    sb = sm.slabB[is];
                 }
                 if (!empty) stale = false;
                 // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
-                const int slo = empty ? sm.g_lo[grp] : is;
-                const int shi = empty ? sm.g_lo[grp + 1] : is + 1;
-                const int l0 = sm.lay0[slo], l1 = sm.lay0[shi];
-                const float zlo = sm.z[l0], zhi = sm.z[l1];
+                float zlo, zhi, M;
+                int slo, shi, l0, l1;
+                if (empty) {
+                    const int4 gb = sm.grpB[grp];
+                    zlo = ga.x; zhi = ga.y; M = ga.z;
+                    slo = gb.x; shi = gb.y; l0 = gb.z; l1 = gb.w;
+                } else {
+                    const float4 sa = sm.slabA[is];
+                    zlo = sa.x; zhi = sa.y;
+                    M = sa.z + __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix);
+                    slo = is; shi = is + 1; l0 = sb.x; l1 = sb.y;
+                }
                 const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
                 const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
                 const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
-                float M;
-                if (empty) M = sm.g_maj1d[grp];
-                else M = sm.maj1d[is] + __ldg(S.maj + (size_t(sm.cz[is]) * S.ncy + p.ciy) * S.ncx + p.cix);
                 // distances to the cell faces along the flight direction (branch-free)
                 const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
                 float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
                 if (p.d.z == 0.0f) tz = RT_INF;
                 float tx = RT_INF, ty = RT_INF;
-                if (in3 && !p.frozen) {
+                if (in3 && !(FZ && p.frozen)) {
                     tx = ((upx ? fminf(float(ixhi) * S.Sx, S.Lx) : float(ixlo) * S.Sx) - p.x) * invd.x;
                     ty = ((upy ? fminf(float(iyhi) * S.Sy, S.Ly) : float(iylo) * S.Sy) - p.y) * invd.y;
                     if (p.d.x == 0.0f) tx = RT_INF;
@@ -574,26 +619,19 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                 const float dmove = hit ? dcol : dexit;
                 const bool zcross = !hit && (tz <= tx) && (tz <= ty);
                 const bool xcross = !hit && !zcross && (tx <= ty);
-                const bool ycross = !hit && !zcross && !xcross;
 
                 // ---- move
                 float zn = p.z + p.d.z * dmove;
                 if (zcross) zn = upz ? zhi : zlo;
-                if (per_level && J.has_abs) {
+                if (PL && (p.jflags & 1)) {
                     // flux / heating targets: weight must be current at every level (cells are single layers here)
                     const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + l0) * dmove);
-                    w_atm += double(p.w) - double(wn);
-                    if (want_heat) {
-                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                        tally_add(S.heat + (size_t(J.slab) * S.nz + l0) * nxy + size_t(hy) * S.nx + hx,
-                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + l0) : 1.0));
-                        ++n_tally;
-                    }
+                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    if (want_heat) heat_tally(S, sm, p, l0, double(p.w) - double(wn));
                     p.w = wn;
                 }
                 p.leg += dmove;
-                if (!p.frozen) {
+                if (!(FZ && p.frozen)) {
                     p.x += p.d.x * dmove; p.y += p.d.y * dmove;
                     if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
                 }
@@ -610,19 +648,19 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                         stale = false;
                         if (upz) {
                             p.iz = l1 - 1;
-                            if (want_flux) flux_tally(S, J, p, 2, l1, n_tally);
+                            if (want_flux) flux_tally(S, sm, p, 2, l1);
                             if (shi >= S.nslab_z) ev = EV_ESC;
                             else { p.is = shi; p.iz = l1; }
                         } else {
                             p.iz = l0;
                             if (want_flux) {
-                                if (p.direct) flux_tally(S, J, p, 0, l0, n_tally);
-                                flux_tally(S, J, p, 1, l0, n_tally);
+                                if (p.direct) flux_tally(S, sm, p, 0, l0);
+                                flux_tally(S, sm, p, 1, l0);
                             }
                             if (slo == 0) ev = EV_SFC;
                             else { p.is = slo - 1; p.iz = l0 - 1; }
                         }
-                        if (ev == EV_NONE && !p.frozen && sm.cz[p.is] >= 0 && (!in3 || empty)) {
+                        if (ev == EV_NONE && !(FZ && p.frozen) && (!in3 || empty) && __float_as_int(sm.slabA[p.is].w) >= 0) {
                             // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
                             int cx = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                             int cy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
@@ -659,15 +697,18 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
         }
 
         // =========================================================== (3) tentative collisions: accept or reject
+        float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ev_s3 = 0.0f, ev_uc = 0.0f;
+        int ev_fx = 0, ev_fy = 0, ev_vox = 0;
         if (alive && ev == EV_TENT) {
-            const float4 u = rng4(g);
+            float4 u;
+            RNG4(u);
             const int izn = p.iz;
             float sig = sm.e1tot[izn];
             float s3 = 0.0f;
-            int fx = 0, fy = 0;
-            size_t vox = 0;
+            int fx = 0, fy = 0, vox = 0;
             if (ev_in3) {
-                if (p.frozen) { fx = p.cix; fy = p.ciy; }
+                if (FZ && p.frozen) { fx = p.cix; fy = p.ciy; }
                 else {
                     const int shx = ev_empty ? S.shx : 0, shy = ev_empty ? S.shy : 0;
                     const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
@@ -675,15 +716,15 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                     fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
                     fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
                 }
-                vox = (size_t(izn - S.iz0) * S.ny + fy) * S.nx + fx;
-                if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; ++n_tent; }
+                vox = ((izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT(CNT_TENT)++; }
             }
             p.tau = -__logf(u.y);
             const float uc = u.x * ev_M;
             if (uc < sig) {
                 ev = EV_COLL;
                 ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox;
-                if (ev_in3 && ev_empty && !p.frozen) {
+                if (ev_in3 && ev_empty && !(FZ && p.frozen)) {
                     // keep the fine cell indices consistent with the position inside the coarse cell
                     p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
                 }
@@ -697,14 +738,14 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
             // ---- path-integrated gas absorption of the leg that ends here
             const int izb = (evk == EV_SFC) ? 0 : (evk == EV_ESC ? S.nz - 1 : p.iz);
             if (evk == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; stale = false; }
-            if (J.has_abs && !per_level) {
+            if (!PL && (p.jflags & 1)) {
                 const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, fabsf(invd.z));
                 const float wn = p.w * __expf(-ta);
-                w_atm += double(p.w) - double(wn);
+                ACC(ACC_ATM) += double(p.w) - double(wn);
                 p.w = wn;
             }
             p.za = p.z; p.iza = izb; p.leg = 0.0f;
-            if (evk == EV_ESC) { w_toa += double(p.w); alive = false; continue; }
+            if (evk == EV_ESC) { ACC(ACC_TOA) += double(p.w); alive = false; continue; }
 
             float4 u;
             float3 newd;
@@ -746,23 +787,17 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                         uc -= e;
                     }
                 }
-                ++n_coll;
+                CNT(CNT_COLL)++;
                 // implicit capture
                 const float wn = p.w * omg;
                 if (wn < p.w) {
-                    w_atm += double(p.w) - double(wn);
-                    if (want_heat) {
-                        const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                        const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                        tally_add(S.heat + (size_t(J.slab) * S.nz + izn) * nxy + size_t(hy) * S.nx + hx,
-                                  (double(p.w) - double(wn)) * J.norm * double(nxy) * (J.has_fscale ? __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + izn) : 1.0));
-                        ++n_tally;
-                    }
+                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
                 }
                 p.w = wn;
                 p.order++; p.direct = false;
                 if (!(p.w > 0.0f)) { alive = false; continue; }
-                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
                     if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
                     else { p.cix = fx; p.ciy = fy; }
                     p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
@@ -770,24 +805,24 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                 }
             } else {
                 // ---- surface hit
-                ++n_sfc;
-                u = rng4(g);
+                CNT(CNT_SFC)++;
+                RNG4(u);
                 int sx, sy;
-                if (p.frozen) {
+                if (FZ && p.frozen) {
                     sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
                     sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
                 } else {
                     sx = min(S.sfc_nx - 1, max(0, int(p.x * S.inv_Lx * float(S.sfc_nx))));
                     sy = min(S.sfc_ny - 1, max(0, int(p.y * S.inv_Ly * float(S.sfc_ny))));
                 }
-                const size_t sn = size_t(S.sfc_nx) * S.sfc_ny, si = size_t(sy) * S.sfc_nx + sx;
+                const int sn = S.sfc_nx * S.sfc_ny, si = sy * S.sfc_nx + sx;
                 sfc_type = __ldg(S.sfc_type + si);
 #pragma unroll
                 for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
                 if (want_rad && S.nz3 > 0 && S.iz0 == 0) {
-                    fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                    fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-                    s3 = __ldg(S.ext3tot + size_t(fy) * S.nx + fx);
+                    fx = (FZ && p.frozen) ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                    fy = (FZ && p.frozen) ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    s3 = __ldg(S.ext3tot + fy * S.nx + fx);
                 }
             }
 
@@ -804,22 +839,22 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
                     } else {
                         f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm, wi, se.s) * se.s.z : 0.0f;
                     }
-                    if (f > 0.0f) le_deposit(S, sm, J, se, p, f * p.w, fx, fy, s3, n_le, n_visit, n_tally);
+                    if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3);
                 }
             }
 
             // ---- new direction
             if (evk == EV_COLL) {
                 float xi_tab = 0.5f;
-                if (apf >= 1.0f) { const float4 v = rng4(g); xi_tab = v.x; }
+                if (apf >= 1.0f) { float4 v; RNG4(v); xi_tab = v.x; }
                 const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
                 newd = rotate_dir(p.d, mu, RT_2PI * u.w);
-                if (p.order >= S.iso_max) { w_rr -= double(p.w); alive = false; continue; }
+                if (p.order >= S.iso_max) { ACC(ACC_RR) -= double(p.w); alive = false; continue; }
             } else {
                 float3 wo;
                 const float fac = surface_sample(sfc_type, prm, wi, u, wo);
                 const float wn = p.w * fac;
-                w_sfc += double(p.w) - double(wn);
+                ACC(ACC_SFC) += double(p.w) - double(wn);
                 p.w = wn;
                 if (!(p.w > 0.0f)) { alive = false; continue; }
                 const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
@@ -829,12 +864,12 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
             p.d = newd;
             invd = inv_dir(p.d);
             if (evk == EV_SFC) {
-                if (want_flux) flux_tally(S, J, p, 2, 0, n_tally);
-                if (S.nz3 > 0 && S.iz0 == 0 && !p.frozen) {
+                if (want_flux) flux_tally(S, sm, p, 2, 0);
+                if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && p.frozen)) {
                     p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                     p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
                 }
-                if (S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
                     p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                     p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
                     p.frozen = true;
@@ -843,17 +878,19 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
             // ---- Russian roulette (Pho_wmin / Pho_wfac), shared
             if (p.w < S.wmin) {
                 float xi = u.w;
-                if (evk == EV_COLL) { const float4 v = rng4(g); xi = v.x; }
-                if (xi * S.wfac < p.w) { w_rr += double(S.wfac) - double(p.w); p.w = S.wfac; }
-                else { w_rr -= double(p.w); ++n_kill; alive = false; continue; }
+                if (evk == EV_COLL) { float4 v; RNG4(v); xi = v.x; }
+                if (xi * S.wfac < p.w) { ACC(ACC_RR) += double(S.wfac) - double(p.w); p.w = S.wfac; }
+                else { ACC(ACC_RR) -= double(p.w); CNT(CNT_KILL)++; alive = false; continue; }
             }
-            if (p.w < 1e-30f) { w_rr -= double(p.w); alive = false; continue; }
+            if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; continue; }
         }
     }
+#undef RNG4
 
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
-    unsigned long long c[9] = {n_phot, n_cell, n_tent, n_coll, n_sfc, n_le, n_visit, n_tally, n_kill};
-    double dsum[4] = {w_toa, w_sfc, w_atm, w_rr};
+    unsigned long long c[9] = {CNT(CNT_PHOT), n_cell, CNT(CNT_TENT), CNT(CNT_COLL), CNT(CNT_SFC), CNT(CNT_LE), CNT(CNT_VISIT),
+                               CNT(CNT_TALLY), CNT(CNT_KILL)};
+    double dsum[4] = {ACC(ACC_TOA), ACC(ACC_SFC), ACC(ACC_ATM), ACC(ACC_RR)};
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -873,6 +910,14 @@ __global__ void __launch_bounds__(256, 2) transport_kernel(const __grid_constant
         atomicAdd(&S.stats->w_toa, dsum[0]); atomicAdd(&S.stats->w_sfc, dsum[1]);
         atomicAdd(&S.stats->w_atm, dsum[2]); atomicAdd(&S.stats->w_rr, dsum[3]);
     }
+}
+#undef ACC
+#undef CNT
+
+typedef void (*transport_fn)(const DevScene);
+static transport_fn pick_transport(bool pl, bool fz) {
+    if (pl) return fz ? transport_kernel<true, true> : transport_kernel<true, false>;
+    return fz ? transport_kernel<false, true> : transport_kernel<false, false>;
 }
 
 // ============================================================================ test-hook kernels
@@ -917,7 +962,8 @@ struct Handle {
     DevScene S{};
     b200rt_options opt{};
     int numSM = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_tables = 0;
+    bool k_pl = false, k_fz = false;
     // owned device memory
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3;
@@ -1080,16 +1126,26 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
 
     // ------------------------------------------------ super-voxel grid
     const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0;
-    int svx = opt->svx > 0 ? opt->svx : 2, svy = opt->svy > 0 ? opt->svy : 2, svz = opt->svz > 0 ? opt->svz : (nz3 > 16 ? 4 : 1);
+    // auto sizes: fine cells of 2 x 2 columns and as many layers as make them roughly cubic; coarse (empty-space)
+    // cells of 4 x 4 fine cells horizontally and about the same physical height (tuned on the config-2 scene,
+    // tools/sweep_sv.py; any choice is unbiased, tests/test_gpu_parity.py sweeps several)
+    int svx = opt->svx > 0 ? opt->svx : 2, svy = opt->svy > 0 ? opt->svy : 2, svz = opt->svz;
+    if (svz <= 0) {
+        svz = 1;
+        if (nz3 > 1) {
+            const double dz_mean = (zg[iz0 + nz3] - zg[iz0]) / nz3;
+            svz = int(std::lround(svx * sc->dx / dz_mean));
+        }
+    }
     if (opt->solver != B200RT_SOLVER_3D) { svx = 1; svy = 1; }     // column-frozen modes need cell == column
     if (per_level) svz = 1;                                       // every z crossing must be a level crossing
     // coarse (emptiness) level: 2^shx x 2^shy fine cells horizontally, cmz fine slabs vertically
     auto log2floor = [](int v) { int s = 0; while ((2 << s) <= v) ++s; return s; };
     int shx = log2floor(std::max(1, opt->cmx > 0 ? opt->cmx : 4)), shy = log2floor(std::max(1, opt->cmy > 0 ? opt->cmy : 4));
-    int cmz = opt->cmz > 0 ? opt->cmz : 8;
+    int cmz = opt->cmz > 0 ? opt->cmz : 5;
     if (per_level) { shx = 0; shy = 0; cmz = 1; }
     S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 16;
-    S.event_min = opt->event_min > 0 ? opt->event_min : 16;
+    S.event_min = opt->event_min > 0 ? opt->event_min : 20;
     S.regen_min = opt->regen_min > 0 ? opt->regen_min : 8;
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
@@ -1163,8 +1219,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.zgrd = (const float*)H->zgrd.p; S.e1tot = (const float*)H->e1tot.p; S.e1cum = (const float*)H->e1cum.p;
     S.e1 = (const float*)H->e1.p; S.o1 = (const float*)H->o1.p; S.a1 = (const float*)H->a1.p;
     S.slab_lay0 = (const int*)H->slab_lay0.p; S.slab_cz = (const int*)H->slab_cz.p; S.slab_maj1d = (const float*)H->slab_maj1d.p;
-    H->smem_bytes = sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz + S.nslab_z + S.ngroup) +
-                    sizeof(int) * (3 * size_t(S.nslab_z) + 1 + 2 * size_t(S.ngroup) + 1);
+    H->smem_tables = 16 * (2 * size_t(S.nslab_z) + 2 * size_t(S.ngroup)) + sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz);
+    H->smem_bytes = H->smem_tables + 256 * (4 * 8 + 8 * 4);
     if (H->smem_bytes > 200 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
 
     // ------------------------------------------------ 3-D block
@@ -1297,6 +1353,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         se.vertical_up = (se.s.x == 0.f && se.s.y == 0.f && se.s.z > 0.f) ? 1 : 0;
         se.fast_ok = (nz3 == 0 || se.zt >= fz[iz0 + nz3]) ? 1 : 0;
         se.off = off;
+        se.npix = double(q.nxr) * double(q.nyr);
         off += (long long)q.nxr * q.nyr;
     }
     S.rad_slab = off;
@@ -1315,8 +1372,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.flux = (double*)H->flux.p; S.rad = (double*)H->rad.p; S.heat = (double*)H->heat.p;
     S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
 
+    H->k_pl = per_level; H->k_fz = (opt->solver != B200RT_SOLVER_3D);
     if (H->smem_bytes > 48 * 1024)
-        CK(cudaFuncSetAttribute(transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->smem_bytes)));
+        CK(cudaFuncSetAttribute(pick_transport(H->k_pl, H->k_fz), cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->smem_bytes)));
     H->opt = *opt;
     H->have_scene = true;
     H->ran = false;
@@ -1346,7 +1404,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
         d.first = acc; d.count = (unsigned long long)cnt; acc += d.count;
         d.seed = q.seed;
         d.norm = q.nphot > 0 ? double(S.mu0) * H->src_flx / double(q.nphot) : 0.0;
-        d.rad_scale = q.rad_scale;
+        d.rad_fac = d.norm * q.rad_scale;
         d.slab = q.slab;
         d.has_abs = 0; d.has_fscale = 0;
         if (q.abs1d) {
@@ -1385,13 +1443,15 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : 256;
     tpb = std::min(256, std::max(32, (tpb / 32) * 32));
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, transport_kernel, tpb, H->smem_bytes));
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz);
+    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));
     if (bps < 1) return fail(H, B200RT_ERR_CUDA, "transport kernel does not fit on an SM");
     if (H->opt.blocks_per_sm > 0) bps = std::min(bps, H->opt.blocks_per_sm);
     unsigned long long want = (acc + tpb - 1) / tpb;
     int grid = int(std::min<unsigned long long>((unsigned long long)H->numSM * bps, std::max<unsigned long long>(1, want)));
     CK(cudaEventRecord(H->ev0, st));
-    transport_kernel<<<grid, tpb, H->smem_bytes, st>>>(S);
+    kern<<<grid, tpb, smem, st>>>(S);
     CK(cudaGetLastError());
     CK(cudaEventRecord(H->ev1, st));
     H->last_stream = st;
