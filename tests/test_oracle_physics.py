@@ -1,0 +1,176 @@
+"""
+Pins for the CPU oracle (oracle/oracle_mc.cpp).  MCARaTS itself is not available offline and the reference ships no
+golden vectors for transport, so the oracle is pinned against
+  * a deterministic adding-doubling solver (oracle/adding_doubling.py): flux profile and nadir radiance,
+  * analytic identities: direct beam, energy conservation, Lambertian surface without atmosphere, single scattering,
+    IPA == 1-D on a horizontally uniform field, BRDF quadrature albedo.
+Tolerances are a few Monte Carlo standard errors at the photon counts used (written next to each assertion).
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+import scenes
+from oracle import adding_doubling as ad
+from er3t_b200 import abi
+
+
+def energy_balance(st):
+    return (st['w_toa_up'] + st['w_sfc_abs'] + st['w_atm_abs'] - st['w_roulette']) / st['photons'] - 1.0
+
+
+def test_against_adding_doubling_flux_profile_and_nadir_radiance():
+    ns = 48
+    mu, w = ad.radau_nodes(ns)
+    k0 = int(np.argmin(abs(mu - 0.85)))
+    mu0 = mu[k0]
+    sza = np.rad2deg(np.arccos(mu0))
+    z = scenes.std_z()
+    nz = z.size - 1
+    ext = np.zeros((2, nz)); omg = np.ones((2, nz)); apf = np.zeros((2, nz))
+    ext[0] = scenes.rayleigh_ext(z); apf[0] = -1.0
+    ext[1, 1] = 8.0 / 1000.0; apf[1, 1] = 0.8; omg[1, 1] = 0.99
+    absg = np.zeros(nz); absg[:5] = 2e-5
+    pr, ph = ad.rayleigh(), ad.hg(0.8)
+    layers = [dict(dz=1000.0, comps=[(ext[0, iz], 1.0, pr), (ext[1, iz], omg[1, iz], ph)], absorb=absg[iz]) for iz in range(nz - 1, -1, -1)]
+    res = ad.solve(layers, 0.2, k0, nstream=ns)
+    sc = abi.HostScene(z, ext, omg, apf, sfc_type=1, sfc_param=(0.2, 0, 0, 0, 0), src_the=180 - sza, src_phi=270.0, src_qmax=0.0,
+                       sensors=[dict(the=180.0, phi=270.0, nxr=1, nyr=1)])
+    opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=1, wmin=0.0)
+    jobs, keep = abi.make_jobs([400000], [7], [0], abs1d=[absg])
+    r = oracle.run(sc, opt, jobs)
+    f = r['flux'][0, :, :, 0, 0]
+    # 4e5 photons: standard error of a flux ~ 8e-4 * mu0; adding-doubling discretisation ~ 2e-4
+    assert np.max(np.abs(f[2] - res['f_up'])) / mu0 < 3.5e-3
+    assert np.max(np.abs(f[1] - res['f_down'])) / mu0 < 3.5e-3
+    assert np.max(np.abs(f[0] - res['f_down_direct'])) / mu0 < 2e-3
+    assert abs(r['rad'][0] / res['rad_nadir_toa'] - 1.0) < 0.01
+    assert abs(energy_balance(r['stats'])) < 1e-10
+
+
+def test_direct_beam_and_energy_conservation_with_roulette():
+    sc, absg = scenes.plane_parallel(cot=3.0, omega=0.9, albedo=0.3, absorb=True, qmax=0.0, with_sensor=False)
+    opt = abi.make_options(target=abi.TARGET_FLUX, nslab=1, wmin=0.2)
+    jobs, keep = abi.make_jobs([300000], [3], [0], abs1d=[absg])
+    r = oracle.run(sc, opt, jobs)
+    st = r['stats']
+    assert abs(energy_balance(st)) < 1e-10                      # fp64 accumulation
+    assert st['n_roulette_kill'] > 0
+    assert abs(st['w_roulette'] / st['photons']) < 5e-3          # roulette is unbiased: created == destroyed weight on average
+    mu0 = np.cos(np.deg2rad(30.0))
+    dz = np.diff(sc.zgrd)
+    tau = np.cumsum(((sc.ext1d.sum(axis=0) + absg) * dz)[::-1])[::-1]      # optical depth from TOA down to each level
+    expect = mu0 * np.exp(-np.concatenate([tau, [0.0]]) / mu0)
+    got = r['flux'][0, 0, :, 0, 0]
+    assert np.max(np.abs(got - expect)) < 3e-3                   # binomial error of 3e5 photons
+
+
+def test_lambertian_surface_without_atmosphere():
+    z = np.array([0.0, 1000.0])
+    sc = abi.HostScene(z, [[1e-12]], [[1.0]], [[-1.0]], sfc_type=1, sfc_param=(0.35, 0, 0, 0, 0), src_the=180.0 - 40.0, src_phi=10.0,
+                       sensors=[dict(the=180.0, phi=270.0, nxr=1, nyr=1), dict(the=180.0 - 50.0, phi=123.0, nxr=1, nyr=1)])
+    opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=1, wmin=0.0)
+    jobs, keep = abi.make_jobs([20000], [1], [0])
+    r = oracle.run(sc, opt, jobs)
+    mu0 = np.cos(np.deg2rad(40.0))
+    assert np.allclose(r['rad'], mu0 * 0.35 / np.pi, rtol=1e-4)      # deterministic up to the solar cone
+    assert np.allclose(r['flux'][0, 2, :, 0, 0], mu0 * 0.35, rtol=1e-4)
+
+
+def test_single_scattering_radiance_analytic():
+    # thin homogeneous HG layer over a black surface: I = mu0 * omega * P(Theta) / (4 pi) * (1 - exp(-tau (1/mu0 + 1/muv))) / (mu0 + muv) ... (mu0 muv form)
+    tau, g, omega = 0.5, 0.6, 0.9
+    z = np.array([0.0, 1000.0])
+    sza, vza = 35.0, 20.0
+    sc = abi.HostScene(z, [[tau / 1000.0]], [[omega]], [[g]], sfc_type=1, sfc_param=(0.0, 0, 0, 0, 0), src_the=180.0 - sza, src_phi=0.0, src_qmax=0.0,
+                       sensors=[dict(the=180.0 - vza, phi=180.0, nxr=1, nyr=1)])
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=1, wmin=0.0, iso_max=1)
+    jobs, keep = abi.make_jobs([400000], [11], [0])
+    r = oracle.run(sc, opt, jobs)
+    mu0, muv = np.cos(np.deg2rad(sza)), np.cos(np.deg2rad(vza))
+    # photon direction (sin sza, 0, -cos sza); toward sensor: -(view) = (sin vza cos(180)*-1 ...) -> computed explicitly
+    d = np.array([np.sin(np.deg2rad(180 - sza)) * 1.0, 0.0, np.cos(np.deg2rad(180 - sza))])
+    v = np.array([np.sin(np.deg2rad(180 - vza)) * np.cos(np.pi), 0.0, np.cos(np.deg2rad(180 - vza))])
+    cosang = float(np.dot(d, -v))
+    P = (1 - g * g) / (1 + g * g - 2 * g * cosang) ** 1.5
+    expect = mu0 * omega * P / (4 * np.pi) * (1 - np.exp(-tau * (1 / mu0 + 1 / muv))) / (muv * (1 / mu0 + 1 / muv)) / mu0
+    assert abs(r['rad'][0] / expect - 1.0) < 0.01
+
+
+def test_ipa_equals_1d_on_uniform_field_and_3d_agrees():
+    z = scenes.std_z(10, 10000.0)
+    nz = 10
+    ext1 = scenes.rayleigh_ext(z)[None, :]
+    e3 = np.full((4, 3, 2), 0.004, dtype=np.float32)
+    kw = dict(nx=4, ny=3, dx=200.0, dy=200.0, iz3l=2, ext3d=e3, omg3d=np.ones_like(e3), apf3d=np.full_like(e3, 0.7),
+              sfc_type=1, sfc_param=(0.1, 0, 0, 0, 0), src_the=140.0, src_phi=30.0, sensors=[dict(the=180.0, phi=270.0, nxr=4, nyr=3)])
+    sc3 = abi.HostScene(z, ext1, np.ones((1, nz)), -np.ones((1, nz)), **kw)
+    # the same medium as two 1-D components
+    ext2 = np.zeros((2, nz)); ext2[0] = ext1[0]; ext2[1, 1:3] = 0.004
+    omg2 = np.ones((2, nz)); apf2 = np.zeros((2, nz)); apf2[0] = -1; apf2[1] = 0.7
+    sc1 = abi.HostScene(z, ext2, omg2, apf2, sfc_type=1, sfc_param=(0.1, 0, 0, 0, 0), src_the=140.0, src_phi=30.0, sensors=[dict(the=180.0, phi=270.0, nxr=1, nyr=1)])
+    res = {}
+    for name, sc, solver in (('3d', sc3, abi.SOLVER_3D), ('ipa', sc3, abi.SOLVER_IPA), ('p3d', sc3, abi.SOLVER_PARTIAL_3D), ('1d', sc1, abi.SOLVER_3D)):
+        opt = abi.make_options(solver=solver, target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=1, wmin=0.0)
+        jobs, keep = abi.make_jobs([150000], [5], [0])
+        r = oracle.run(sc, opt, jobs)
+        res[name] = (r['rad'].mean(), r['flux'][0, 2, -1].mean(), r['flux'][0, 1, 0].mean())
+    for name in ('3d', 'ipa', 'p3d'):
+        for a, b in zip(res[name], res['1d']):
+            assert abs(a / b - 1.0) < 0.012, (name, a, b)        # ~3 sigma at 1.5e5 photons
+
+
+@pytest.mark.parametrize('kind', ['lsrt', 'dsm'])
+def test_brdf_sampling_matches_quadrature_albedo(kind):
+    """surface_sample weights (oracle) integrate to the albedo obtained by quadrature of the BRDF the local estimate uses."""
+    lib = oracle.load()
+    if kind == 'lsrt':
+        t, prm = abi.SFC_LSRT, np.array([0.2, 0.03, 0.1, 0, 0], dtype=np.float32)
+    else:
+        t, prm = abi.SFC_DSM, np.array([0.22, 0.05, 1.34, 1e-7, 0.04], dtype=np.float32)
+    sza = 50.0
+    mu0 = np.cos(np.deg2rad(sza))
+    # quadrature over the upper hemisphere
+    nmu, nphi = 400, 720
+    mu = (np.arange(nmu) + 0.5) / nmu
+    phi = (np.arange(nphi) + 0.5) * 2 * np.pi / nphi
+    MU, PH = np.meshgrid(mu, phi, indexing='ij')
+    st = np.sqrt(1 - MU ** 2)
+    dout = np.stack([st * np.cos(PH), st * np.sin(PH), MU], axis=-1).reshape(-1, 3)
+    din = np.tile(np.array([np.sin(np.deg2rad(sza)), 0.0, -mu0]), (dout.shape[0], 1))
+    f = np.zeros(dout.shape[0])
+    lib.oracle_brdf_eval(t, prm.ctypes.data, np.ascontiguousarray(din).ctypes.data, np.ascontiguousarray(dout).ctypes.data, f.ctypes.data, f.size)
+    albedo = np.sum(f.reshape(nmu, nphi) * MU) * (1.0 / nmu) * (2 * np.pi / nphi)
+    z = np.array([0.0, 100.0])
+    sc = abi.HostScene(z, [[1e-12]], [[1.0]], [[-1.0]], sfc_type=np.full((1, 1), t, dtype=np.int32), sfc_param=prm.reshape(1, 1, 5),
+                       src_the=180.0 - sza, src_phi=0.0, src_qmax=0.0)
+    opt = abi.make_options(target=abi.TARGET_FLUX, nslab=1, wmin=0.0)
+    jobs, keep = abi.make_jobs([400000], [2], [0])
+    r = oracle.run(sc, opt, jobs)
+    got = r['flux'][0, 2, -1, 0, 0] / mu0
+    assert abs(got / albedo - 1.0) < 0.01, (got, albedo)
+
+
+def test_tabulated_phase_function_sampling_is_consistent_with_evaluation():
+    lib = oracle.load()
+    ang, pha = scenes.synthetic_mie_table()
+    sc = abi.HostScene(np.array([0.0, 1.0]), [[0.0]], [[1.0]], [[0.0]], ang=ang, pha=pha)
+    xi = (np.arange(200000) + 0.5) / 200000
+    mu_s = np.zeros_like(xi)
+    lib.oracle_phase_sample(C.addressof(sc.struct), 2.0, xi.ctypes.data, mu_s.ctypes.data, xi.size)
+    edges = np.linspace(-1, 1, 41)
+    hist, _ = np.histogram(mu_s, bins=edges)
+    mid = np.linspace(-1, 1, 4001)
+    p = np.zeros_like(mid)
+    lib.oracle_phase_eval(C.addressof(sc.struct), 2.0, mid.ctypes.data, p.ctypes.data, mid.size)
+    assert abs(np.trapezoid(p, mid) - 2.0) < 2e-3                     # normalisation (1/2) int P dmu = 1
+    cdf = np.concatenate([[0], np.cumsum(0.5 * (p[1:] + p[:-1]) * np.diff(mid))]) / 2.0
+    expect = np.diff(np.interp(edges, mid, cdf)) * xi.size
+    big = expect > 200
+    assert np.max(np.abs(hist[big] / expect[big] - 1.0)) < 0.02
+    g_sample = mu_s.mean()
+    g_eval = 0.5 * np.trapezoid(p * mid, mid)
+    assert abs(g_sample - g_eval) < 2e-3
