@@ -35,7 +35,7 @@ class Sensor(C.Structure):
 class SceneStruct(C.Structure):
     _fields_ = [('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
                 ('iz3l', C.c_int32), ('nz3', C.c_int32),
-                ('np1d', C.c_int32), ('np3d', C.c_int32), ('_pad0', C.c_int32),
+                ('np1d', C.c_int32), ('np3d', C.c_int32), ('layout3d', C.c_int32),
                 ('dx', C.c_double), ('dy', C.c_double),
                 ('zgrd', C.c_void_p),
                 ('ext1d', C.c_void_p), ('omg1d', C.c_void_p), ('apf1d', C.c_void_p),
@@ -187,11 +187,13 @@ class HostScene:
                 a3 = a3[..., np.newaxis]
             if e3.shape[0] != nx or e3.shape[1] != ny or o3.shape != e3.shape or a3.shape != e3.shape:
                 raise ValueError('Error [HostScene]: 3-D fields must have shape (nx, ny, nz3[, np3d]).')
-            # (nx, ny, nz3, np3d) -> [np3d][nz3][ny][nx]
-            self.ext3d = _arr(np.transpose(e3, (3, 2, 1, 0)), np.float32)
-            self.omg3d = _arr(np.transpose(o3, (3, 2, 1, 0)), np.float32)
-            self.apf3d = _arr(np.transpose(a3, (3, 2, 1, 0)), np.float32)
-            s.np3d, s.nz3 = self.ext3d.shape[0], self.ext3d.shape[1]
+            # zero-copy when the arrays are already float32 and C-contiguous (what mca_atm_3d produces): the library
+            # transposes (nx, ny, nz3, np3d) -> [np3d][nz3][ny][nx] on the GPU (layout3d = 1)
+            self.ext3d = _arr(e3, np.float32)
+            self.omg3d = _arr(o3, np.float32)
+            self.apf3d = _arr(a3, np.float32)
+            s.layout3d = 1
+            s.np3d, s.nz3 = self.ext3d.shape[3], self.ext3d.shape[2]
             s.iz3l = int(iz3l)
             s.ext3d, s.omg3d, s.apf3d = _ptr(self.ext3d), _ptr(self.omg3d), _ptr(self.apf3d)
             if abs3d is not None and np.any(np.asarray(abs3d) != 0.0):

@@ -115,19 +115,26 @@ struct DevScene {
 };
 
 // ============================================================================ setup kernels
+// layout 0: [np3d][nz3][ny][nx] (x fastest, the byte order of the reference's binary file, mca_atm.py:383-388)
+// layout 1: numpy C order of the reference's in-memory arrays (nx, ny, nz3, np3d) (mca_atm.py:248-252): no host transpose
 __global__ void pack_scene_kernel(const float* __restrict__ ext, const float* __restrict__ omg,
-                                  const float* __restrict__ apf, int np3d, size_t nvox,
-                                  float* __restrict__ ext3tot, float2* __restrict__ prop3, int* __restrict__ bad) {
+                                  const float* __restrict__ apf, int np3d, int nx, int ny, int nz3, int layout,
+                                  float* __restrict__ ext3tot, float2* __restrict__ prop3, float* __restrict__ ext3,
+                                  int* __restrict__ bad) {
+    const size_t nvox = size_t(nz3) * ny * nx;
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+        const int ix = int(v % nx), iy = int((v / nx) % ny), k = int(v / (size_t(nx) * ny));
         float tot = 0.0f;
-        for (int k = 0; k < np3d; ++k) {
-            const float e = ext[size_t(k) * nvox + v];
-            const float o = omg[size_t(k) * nvox + v];
-            const float a = apf[size_t(k) * nvox + v];
+        for (int c = 0; c < np3d; ++c) {
+            const size_t src = layout == 0 ? size_t(c) * nvox + v : ((size_t(ix) * ny + iy) * nz3 + k) * np3d + c;
+            const float e = ext[src];
+            const float o = omg[src];
+            const float a = apf[src];
             if (!(e >= 0.0f) || !(o >= 0.0f && o <= 1.0f) || !isfinite(a)) atomicOr(bad, 1);
             tot += e;
-            prop3[size_t(k) * nvox + v] = make_float2(o, a);
+            prop3[size_t(c) * nvox + v] = make_float2(o, a);
+            if (ext3) ext3[size_t(c) * nvox + v] = e;
         }
         ext3tot[v] = tot;
     }
@@ -158,6 +165,15 @@ __global__ void empty_kernel(const float* __restrict__ maj, int ncx, int ncy, in
             for (int kx = Cx << shx; kx < min(ncx, (Cx + 1) << shx); ++kx)
                 m = fmaxf(m, maj[(size_t(kz) * ncy + ky) * ncx + kx]);
     empty3[c] = m > 0.0f ? 0 : 1;
+}
+
+// fold the emptiness flag into the fine majorant grid: cells inside an empty coarse cell get a negative majorant
+__global__ void mark_empty_kernel(float* __restrict__ maj, int ncx, int ncy, int ncz, int shx, int shy, int nCx, int nCy,
+                                  const int* __restrict__ fine2coarse_z, const unsigned char* __restrict__ empty3) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncx * ncy * ncz) return;
+    const int cix = c % ncx, ciy = (c / ncx) % ncy, ciz = c / (ncx * ncy);
+    if (empty3[(fine2coarse_z[ciz] * nCy + (ciy >> shy)) * nCx + (cix >> shx)]) maj[c] = -1.0f;
 }
 
 __global__ void tau_up_kernel(const float* __restrict__ ext3tot, const float* __restrict__ zgrd, int iz0, int nx, int ny,
@@ -563,16 +579,14 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
         for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
             if (alive && ev == EV_NONE) {
                 int is = p.is;
+                float4 sa = sm.slabA[is];                   // zlo, zhi, 1-D majorant, fine z index in the majorant grid
                 int4 sb = sm.slabB[is];                     // l0, l1, group
+                const bool in3 = __float_as_int(sa.w) >= 0;
+                // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
+                float mj = 0.0f;
+                if (in3) { mj = __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix); ++n_cell; }
                 const int grp = sb.z;
-                const float4 ga = sm.grpA[grp];             // zlo, zhi, maj1d, gcz
-                const int gcz = __float_as_int(ga.w);
-                const bool in3 = gcz >= 0;
-                bool empty = !in3;
-                if (in3) {
-                    empty = __ldg(S.empty3 + (gcz * S.nCy + (p.ciy >> S.shy)) * S.nCx + (p.cix >> S.shx)) != 0;
-                    ++n_cell;
-                }
+                const bool empty = !in3 || mj < 0.0f;
                 if (!PL && !empty && stale) {
                     // entered a non-empty coarse cell sideways: find the fine z slab of the current height
                     const int4 gb = sm.grpB[grp];
@@ -582,20 +596,21 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                         if (p.z >= sm.slabA[mid].x) lo = mid; else hi = mid - 1;
                     }
                     is = lo; p.is = lo;
-                    sb = sm.slabB[is];
+                    sa = sm.slabA[is]; sb = sm.slabB[is];
+                    mj = fmaxf(0.0f, __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix));
                 }
                 if (!empty) stale = false;
                 // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
                 float zlo, zhi, M;
                 int slo, shi, l0, l1;
                 if (empty) {
+                    const float4 ga = sm.grpA[grp];         // zlo, zhi, 1-D majorant of the group
                     const int4 gb = sm.grpB[grp];
                     zlo = ga.x; zhi = ga.y; M = ga.z;
                     slo = gb.x; shi = gb.y; l0 = gb.z; l1 = gb.w;
                 } else {
-                    const float4 sa = sm.slabA[is];
                     zlo = sa.x; zhi = sa.y;
-                    M = sa.z + __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix);
+                    M = sa.z + mj;
                     slo = is; shi = is + 1; l0 = sb.x; l1 = sb.y;
                 }
                 const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
@@ -967,6 +982,7 @@ struct Handle {
     // owned device memory
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3;
+    DevBuf st_e, st_o, st_a, f2c;
     DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
     DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
     DevBuf flux, rad, heat;
@@ -1068,7 +1084,7 @@ int b200rt_destroy(void* handle) {
     if (!H) return B200RT_ERR_ARG;
     cudaSetDevice(H->device);
     DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
-                     &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3,
+                     &H->st_e, &H->st_o, &H->st_a, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3,
                      &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
                      &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
                      &H->flux, &H->rad, &H->heat};
@@ -1098,6 +1114,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     if (nz3 > 0 && (sc->np3d < 1 || !sc->ext3d || !sc->omg3d || !sc->apf3d)) return fail(H, B200RT_ERR_ARG, "3-D block without fields");
     if (sc->abs3d) return fail(H, B200RT_ERR_ARG, "Atm_abst3d != 0 is not supported by the CUDA path yet");
     if (sc->nrad < 0 || sc->nrad > MAX_SENS) return fail(H, B200RT_ERR_ARG, "nrad out of range (max 16)");
+    if (sc->layout3d != 0 && sc->layout3d != 1) return fail(H, B200RT_ERR_ARG, "layout3d must be 0 or 1");
     if (opt->nslab < 1) return fail(H, B200RT_ERR_ARG, "nslab must be >= 1");
     if (opt->solver < 0 || opt->solver > 2) return fail(H, B200RT_ERR_ARG, "unknown solver mode");
     if (opt->shard_world < 1 || opt->shard_rank < 0 || opt->shard_rank >= opt->shard_world) return fail(H, B200RT_ERR_ARG, "bad shard rank/world");
@@ -1188,7 +1205,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     lay0.push_back(nz);
     // coarse z groups: runs of 1-D slabs are merged into one group each (unless every level must be visited);
     // the 3-D block is cut into groups of cmz fine slabs.  A group never mixes 1-D and 3-D slabs.
-    std::vector<int> cg(S.nslab_z), g_lo, g_cz, gz_lo;
+    std::vector<int> cg(S.nslab_z), g_lo, g_cz, gz_lo, f2c(std::max(1, S.ncz), 0);
     std::vector<float> g_maj1d;
     {
         int ncoarse3 = 0;
@@ -1206,13 +1223,14 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         }
         g_lo.push_back(S.nslab_z);
         gz_lo.push_back(S.ncz);
+        for (int K = 0; K + 1 < int(gz_lo.size()); ++K) for (int q = gz_lo[K]; q < gz_lo[K + 1]; ++q) f2c[q] = K;
         S.ngroup = int(g_cz.size());
     }
     if ((rc = upload(H, H->zgrd, fz)) || (rc = upload(H, H->e1tot, fe1tot)) || (rc = upload(H, H->e1cum, fe1cum)) ||
         (rc = upload(H, H->e1, fe1)) || (rc = upload(H, H->o1, fo1)) || (rc = upload(H, H->a1, fa1)) ||
         (rc = upload(H, H->slab_lay0, lay0)) || (rc = upload(H, H->slab_cz, czv)) || (rc = upload(H, H->slab_maj1d, maj1d)) ||
         (rc = upload(H, H->slab_cg, cg)) || (rc = upload(H, H->group_lo, g_lo)) || (rc = upload(H, H->group_cz, g_cz)) ||
-        (rc = upload(H, H->group_maj1d, g_maj1d)) || (rc = upload(H, H->gz_lo, gz_lo)))
+        (rc = upload(H, H->group_maj1d, g_maj1d)) || (rc = upload(H, H->gz_lo, gz_lo)) || (rc = upload(H, H->f2c, f2c)))
         return rc;
     S.slab_cg = (const int*)H->slab_cg.p; S.group_lo = (const int*)H->group_lo.p; S.group_cz = (const int*)H->group_cz.p;
     S.group_maj1d = (const float*)H->group_maj1d.p;
@@ -1231,41 +1249,40 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
             (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->empty3, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1))) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
             (rc = dev_alloc(H, H->flag, 16)))
             return rc;
-        // stage the caller's arrays on the device when they are host pointers
-        DevBuf st_e, st_o, st_a;
+        // stage the caller's arrays on the device when they are host pointers (staging buffers are kept by the handle
+        // so that repeated uploads do not pay cudaMalloc/cudaFree)
         const float *de = sc->ext3d, *dom = sc->omg3d, *da = sc->apf3d;
-        if (sc->np3d > 1) {
-            if ((rc = dev_alloc(H, H->ext3, nall * 4))) return rc;
-            CK(cudaMemcpy(H->ext3.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
-            de = (const float*)H->ext3.p;
-        } else if (!is_device_ptr(sc->ext3d)) {
-            if ((rc = dev_alloc(H, st_e, nall * 4))) return rc;
-            CK(cudaMemcpy(st_e.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
-            de = (const float*)st_e.p;
+        if (!is_device_ptr(sc->ext3d)) {
+            if ((rc = dev_alloc(H, H->st_e, nall * 4))) return rc;
+            CK(cudaMemcpy(H->st_e.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
+            de = (const float*)H->st_e.p;
         }
         if (!is_device_ptr(sc->omg3d)) {
-            if ((rc = dev_alloc(H, st_o, nall * 4))) { st_e.release(); return rc; }
-            CK(cudaMemcpy(st_o.p, sc->omg3d, nall * 4, cudaMemcpyDefault));
-            dom = (const float*)st_o.p;
+            if ((rc = dev_alloc(H, H->st_o, nall * 4))) return rc;
+            CK(cudaMemcpy(H->st_o.p, sc->omg3d, nall * 4, cudaMemcpyDefault));
+            dom = (const float*)H->st_o.p;
         }
         if (!is_device_ptr(sc->apf3d)) {
-            if ((rc = dev_alloc(H, st_a, nall * 4))) { st_e.release(); st_o.release(); return rc; }
-            CK(cudaMemcpy(st_a.p, sc->apf3d, nall * 4, cudaMemcpyDefault));
-            da = (const float*)st_a.p;
+            if ((rc = dev_alloc(H, H->st_a, nall * 4))) return rc;
+            CK(cudaMemcpy(H->st_a.p, sc->apf3d, nall * 4, cudaMemcpyDefault));
+            da = (const float*)H->st_a.p;
         }
+        if (sc->np3d > 1) { if ((rc = dev_alloc(H, H->ext3, nall * 4))) return rc; }
         CK(cudaMemset(H->flag.p, 0, 16));
         const int nb = int(std::min<size_t>((nvox + 255) / 256, size_t(H->numSM) * 16));
-        pack_scene_kernel<<<nb, 256>>>(de, dom, da, sc->np3d, nvox, (float*)H->ext3tot.p, (float2*)H->prop3.p, (int*)H->flag.p);
+        pack_scene_kernel<<<nb, 256>>>(de, dom, da, sc->np3d, sc->nx, sc->ny, nz3, sc->layout3d, (float*)H->ext3tot.p, (float2*)H->prop3.p,
+                                       sc->np3d > 1 ? (float*)H->ext3.p : nullptr, (int*)H->flag.p);
         const int ncell = S.ncx * S.ncy * S.ncz;
         majorant_kernel<<<(ncell + 127) / 128, 128>>>((const float*)H->ext3tot.p, sc->nx, sc->ny, nz3, svx, svy, svz, S.ncx, S.ncy, S.ncz, (float*)H->maj.p);
         const int nC = S.nCx * S.nCy * int(gz_lo.size() - 1);
         empty_kernel<<<(nC + 127) / 128, 128>>>((const float*)H->maj.p, S.ncx, S.ncy, shx, shy, S.nCx, S.nCy, int(gz_lo.size() - 1),
                                                  (const int*)H->gz_lo.p, (unsigned char*)H->empty3.p);
+        mark_empty_kernel<<<(ncell + 127) / 128, 128>>>((float*)H->maj.p, S.ncx, S.ncy, S.ncz, shx, shy, S.nCx, S.nCy, (const int*)H->f2c.p,
+                                                          (const unsigned char*)H->empty3.p);
         const int ncol = sc->nx * sc->ny;
         tau_up_kernel<<<(ncol + 127) / 128, 128>>>((const float*)H->ext3tot.p, S.zgrd, iz0, sc->nx, sc->ny, nz3, (float*)H->tu3.p);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
-        st_e.release(); st_o.release(); st_a.release();
         int bad = 0;
         CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (bad) return fail(H, B200RT_ERR_ARG, "3-D field out of range (need ext >= 0, 0 <= omg <= 1, finite apf)");

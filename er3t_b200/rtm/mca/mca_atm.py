@@ -14,7 +14,7 @@ import warnings
 
 import numpy as np
 
-from er3t_b200.util import cal_mol_ext, get_lay_index
+from er3t_b200.util import cal_mol_ext, get_lay_index, host_zeros
 
 __all__ = ['mca_atm_1d', 'mca_atm_3d']
 
@@ -143,10 +143,12 @@ class mca_atm_3d:
         ext_in = ext_in.data if isinstance(ext_in, np.ma.MaskedArray) else np.asarray(ext_in)
         atm_tmp = np.asarray(cld['temperature']['data'], dtype=np.float32) - atm['temperature']['data'][lay_index].astype(np.float32)[None, None, :]
         atm_abs = np.zeros((nx, ny, nz3, 1), dtype=np.float32)
-        atm_ext = np.zeros((nx, ny, nz3, 1), dtype=np.float32)
+        # the three fields the solver reads live in page-locked memory when a GPU is present (fast H2D)
+        atm_ext = host_zeros((nx, ny, nz3, 1), np.float32)
         atm_ext[..., 0] = ext_in[:, :, :nz3]
-        atm_omg = np.ones((nx, ny, nz3, 1), dtype=np.float32)
-        atm_apf = np.zeros((nx, ny, nz3, 1), dtype=np.float32)
+        atm_omg = host_zeros((nx, ny, nz3, 1), np.float32)
+        atm_omg[...] = 1.0
+        atm_apf = host_zeros((nx, ny, nz3, 1), np.float32)
 
         if self.pha is None:
             atm_apf[...] = 0.85

@@ -8,7 +8,7 @@ import datetime
 import numpy as np
 
 __all__ = ['cal_sol_fac', 'cal_mol_ext', 'cal_mol_ext_0', 'g0_calc', 'g_alt_calc', 'get_lay_index', 'nice_array_str',
-           'cal_r_twostream', 'cal_t_twostream', 'cal_ext', 'add_reference', 'print_reference']
+           'cal_r_twostream', 'cal_t_twostream', 'cal_ext', 'add_reference', 'print_reference', 'host_zeros']
 
 _references = []
 
@@ -115,6 +115,19 @@ def cal_ext(cot, cer, dz=1.0, Qe=2.0):
     lwp = 2.0 / 3000.0 * cot * cer
     lwc = lwp / dz
     return 0.75 * Qe * lwc / cer * 1.0e3
+
+
+def host_zeros(shape, dtype=np.float32):
+    """Zero-filled host array; page-locked (pinned) when a CUDA device is present so that the host -> device copy of the
+    3-D fields in b200rt_upload_scene runs at full PCIe speed.  Falls back to plain numpy memory otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+            return torch.zeros(tuple(shape), dtype=tdt, pin_memory=True).numpy()
+    except Exception:
+        pass
+    return np.zeros(shape, dtype=dtype)
 
 
 def default_date():

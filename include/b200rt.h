@@ -75,7 +75,9 @@ typedef struct b200rt_scene {
     int32_t nx, ny, nz;
     int32_t iz3l, nz3;            /* nz3 == 0: no 3-D block                                    */
     int32_t np1d, np3d;           /* Atm_np1d, Atm_np3d                                        */
-    int32_t _pad0;
+    int32_t layout3d;             /* memory order of ext3d/omg3d/apf3d: 0 = [np3d][nz3][ny][nx] (the reference's file
+                                     order, x fastest); 1 = C order of the reference's in-memory arrays
+                                     (nx, ny, nz3, np3d) (mca_atm.py:248-252), transposed on the GPU */
     double  dx, dy;               /* m                                                         */
     const double* zgrd;           /* [nz+1] level heights, m, strictly increasing              */
     /* 1-D components, mca_atm.py:85-139 */
@@ -83,9 +85,9 @@ typedef struct b200rt_scene {
     const double* omg1d;          /* [np1d][nz]                                                */
     const double* apf1d;          /* [np1d][nz]  -1 Rayleigh | (-1,1) HG g | >=1 table index   */
     /* 3-D components, mca_atm.py:248-337 (float32 exactly as the reference stores them) */
-    const float*  ext3d;          /* [np3d][nz3][ny][nx] 1/m                                   */
-    const float*  omg3d;          /* [np3d][nz3][ny][nx]                                       */
-    const float*  apf3d;          /* [np3d][nz3][ny][nx]                                       */
+    const float*  ext3d;          /* 1/m, see layout3d                                         */
+    const float*  omg3d;
+    const float*  apf3d;
     const float*  abs3d;          /* [nz3][ny][nx] absorption perturbation 1/m, may be NULL    */
     /* tabulated phase functions, mca_sca.py:82-95 */
     int32_t npf, nang;            /* Sca_npf, Sca_nangi (npf == 0: none)                       */

@@ -301,10 +301,17 @@ struct Scene {
     int solver, target;
     double wmin, wfac; int iso_ss, iso_max;
     inline bool in3d(int iz) const { return nz3 > 0 && iz >= iz0 && iz < iz0 + nz3; }
+    int layout = 0;   // b200rt_scene.layout3d
     inline size_t vox(int iz, int iy, int ix) const { return (size_t(iz - iz0) * ny + iy) * nx + ix; }
+    // index of component k of voxel (iz, iy, ix) in the caller's 3-D arrays
+    inline size_t idx3(int k, int iz, int iy, int ix) const {
+        if (layout == 0) return size_t(k) * nz3 * ny * nx + vox(iz, iy, ix);
+        return ((size_t(ix) * ny + iy) * nz3 + (iz - iz0)) * np3d_in + k;
+    }
+    int np3d_in = 0;
     inline double ext3tot(int iz, int iy, int ix) const {
-        double s = 0; const size_t n3 = size_t(nz3) * ny * nx; const size_t v = vox(iz, iy, ix);
-        for (int k = 0; k < np3d; ++k) s += double(e3[k * n3 + v]);
+        double s = 0;
+        for (int k = 0; k < np3d; ++k) s += double(e3[idx3(k, iz, iy, ix)]);
         return s;
     }
 };
@@ -549,16 +556,15 @@ void trace_photon(const Scene& S, const JobCtx& J, const Tally& T, Philox& R, Co
             const bool is3 = S.in3d(iz);
             // choose component with probability ext_k / sum ext
             double sig = S.e1tot[iz];
-            const size_t n3 = size_t(S.nz3) * S.ny * S.nx;
-            size_t v = 0;
-            if (is3) { v = S.vox(iz, p.iy, p.ix); sig += S.ext3tot(iz, p.iy, p.ix); }
+            if (is3) sig += S.ext3tot(iz, p.iy, p.ix);
             double u = R.uni() * sig;
             double omg = 1.0, apf = 0.0;
             bool found = false;
             if (is3) {
                 for (int k = 0; k < S.np3d && !found; ++k) {
-                    const double e = S.e3[k * n3 + v];
-                    if (u < e) { omg = S.o3[k * n3 + v]; apf = S.a3[k * n3 + v]; found = true; }
+                    const size_t q = S.idx3(k, iz, p.iy, p.ix);
+                    const double e = S.e3[q];
+                    if (u < e) { omg = S.o3[q]; apf = S.a3[q]; found = true; }
                     else u -= e;
                 }
             }
@@ -711,6 +717,7 @@ int oracle_run(const b200rt_scene* sc, const b200rt_options* opt, const b200rt_j
     S.e1tot.assign(S.nz, 0.0);
     for (int k = 0; k < S.np1d; ++k) for (int i = 0; i < S.nz; ++i) S.e1tot[i] += S.e1[size_t(k) * S.nz + i];
     S.e3 = sc->ext3d; S.o3 = sc->omg3d; S.a3 = sc->apf3d; S.abs3 = sc->abs3d;
+    S.layout = sc->layout3d; S.np3d_in = sc->np3d;
     build_phase(sc, S.phase);
     S.sfc_nx = sc->sfc_nx; S.sfc_ny = sc->sfc_ny; S.sfc_type = sc->sfc_type; S.sfc_param = sc->sfc_param;
     S.src = dir_from_angles(sc->src_the, sc->src_phi);

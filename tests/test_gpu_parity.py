@@ -198,7 +198,7 @@ def test_cyclic_shift_invariance(solver):
     opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
     jobs, keep = scenes.multi_seed_jobs(200000, nslab)
     solver.upload_scene(sc, opt); solver.run(jobs); a = solver.read_rad().reshape(nslab, 12, 16)
-    ext = np.transpose(sc.ext3d, (3, 2, 1, 0)); omg = np.transpose(sc.omg3d, (3, 2, 1, 0)); apf = np.transpose(sc.apf3d, (3, 2, 1, 0))
+    ext, omg, apf = sc.ext3d, sc.omg3d, sc.apf3d          # (nx, ny, nz3, np3d)
     sh = (5, 3)
     sc2 = abi.HostScene(sc.zgrd, sc.ext1d, sc.omg1d, sc.apf1d, nx=16, ny=12, dx=100.0, dy=100.0, iz3l=sc.struct.iz3l,
                         ext3d=np.roll(ext, sh, axis=(0, 1)), omg3d=np.roll(omg, sh, axis=(0, 1)), apf3d=np.roll(apf, sh, axis=(0, 1)),
