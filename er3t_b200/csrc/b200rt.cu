@@ -21,6 +21,9 @@
 #include <vector>
 
 #define MAX_SENS 16
+#ifndef RT_MINB
+#define RT_MINB 2   // resident 256-thread blocks per SM the register allocation aims at
+#endif
 
 // ============================================================================ device structs
 struct DevSensor {
@@ -198,6 +201,7 @@ __global__ void check_finite_kernel(const double* __restrict__ a, size_t n, int*
 }
 
 // ============================================================================ transport kernel
+// Shared-memory view of one thread block: 1-D tables, per-thread accumulators and the per-warp photon pools.
 struct Smem {
     const float* z;       // [nz+1]
     const float* e1tot;   // [nz]
@@ -218,6 +222,7 @@ enum { CNT_PHOT = 0, CNT_TENT = 1, CNT_COLL = 2, CNT_SFC = 3, CNT_LE = 4, CNT_VI
 #define ACC(k) sm.acc[(k) * blockDim.x + threadIdx.x]
 #define CNT(k) sm.cnt[(k) * blockDim.x + threadIdx.x]
 
+// A photon in registers (while a lane works on it).  Between phases it lives in its warp's shared-memory pool.
 struct Photon {
     float x, y, z;
     float3 d;
@@ -228,14 +233,51 @@ struct Photon {
     int iz;           // layer of the last event / crossing
     int order;
     int job;
-    int jflags;       // bit 0: job has gas absorption, bit 1: job has per-level scale factors
+    int flags;        // FL_*
     float za;         // start of the current straight leg (for path-integrated gas absorption)
     int iza;
     float leg;        // length of the current leg
-    bool direct, frozen;
+    uint32_t rc0, rc1, rc2;   // Philox counter: global photon index (lo, hi), draw number
+    float M;          // majorant of the cell in which the photon parked at a tentative collision
 };
+enum { FL_DIRECT = 1, FL_FROZEN = 2, FL_STALE = 4, FL_ABS = 8, FL_FSCALE = 16, FL_IN3 = 32, FL_EMPTY = 64 };
 
+// pool record: NFIELD 32-bit words per slot, structure-of-arrays ([field][slot]) so that lanes touch distinct banks
+enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_JOB, F_ZA, F_LEG, F_RC0, F_RC1, F_RC2, F_M, NFIELD };
+// slot states.  FLY: waiting for the flight phase; TENT / SFC / ESC: parked at an event, waiting for the event phase
+enum { TAG_DEAD = 0, TAG_FLY = 1, TAG_TENT = 2, TAG_SFC = 3, TAG_ESC = 4 };
 enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3, EV_TENT = 4 };
+
+template <int NP>
+__device__ __forceinline__ void pool_load(const float* __restrict__ f, int s, Photon& p) {
+    p.x = f[F_X * NP + s]; p.y = f[F_Y * NP + s]; p.z = f[F_Z * NP + s];
+    p.d.x = f[F_DX * NP + s]; p.d.y = f[F_DY * NP + s]; p.d.z = f[F_DZ * NP + s];
+    p.w = f[F_W * NP + s]; p.tau = f[F_TAU * NP + s];
+    const unsigned c = __float_as_uint(f[F_CELL * NP + s]);
+    p.cix = int(c & 0xffffu); p.ciy = int(c >> 16);
+    const unsigned l = __float_as_uint(f[F_LAY * NP + s]);
+    p.is = int(l & 0xffffu); p.iz = int(l >> 16);
+    const unsigned o = __float_as_uint(f[F_ORD * NP + s]);
+    p.flags = int(o & 0xffu); p.order = int(o >> 8);
+    const unsigned j = __float_as_uint(f[F_JOB * NP + s]);
+    p.job = int(j & 0xffffu); p.iza = int(j >> 16);
+    p.za = f[F_ZA * NP + s]; p.leg = f[F_LEG * NP + s];
+    p.rc0 = __float_as_uint(f[F_RC0 * NP + s]); p.rc1 = __float_as_uint(f[F_RC1 * NP + s]); p.rc2 = __float_as_uint(f[F_RC2 * NP + s]);
+    p.M = f[F_M * NP + s];
+}
+template <int NP>
+__device__ __forceinline__ void pool_store(float* __restrict__ f, int s, const Photon& p) {
+    f[F_X * NP + s] = p.x; f[F_Y * NP + s] = p.y; f[F_Z * NP + s] = p.z;
+    f[F_DX * NP + s] = p.d.x; f[F_DY * NP + s] = p.d.y; f[F_DZ * NP + s] = p.d.z;
+    f[F_W * NP + s] = p.w; f[F_TAU * NP + s] = p.tau;
+    f[F_CELL * NP + s] = __uint_as_float(unsigned(p.cix) | (unsigned(p.ciy) << 16));
+    f[F_LAY * NP + s] = __uint_as_float(unsigned(p.is) | (unsigned(p.iz) << 16));
+    f[F_ORD * NP + s] = __uint_as_float(unsigned(p.flags) | (unsigned(p.order) << 8));
+    f[F_JOB * NP + s] = __uint_as_float(unsigned(p.job) | (unsigned(p.iza) << 16));
+    f[F_ZA * NP + s] = p.za; f[F_LEG * NP + s] = p.leg;
+    f[F_RC0 * NP + s] = __uint_as_float(p.rc0); f[F_RC1 * NP + s] = __uint_as_float(p.rc1); f[F_RC2 * NP + s] = __uint_as_float(p.rc2);
+    f[F_M * NP + s] = p.M;
+}
 
 __device__ __forceinline__ float wrapf(float x, float L, float invL) {
     x -= L * floorf(x * invL);
@@ -246,29 +288,40 @@ __device__ __forceinline__ float wrapf(float x, float L, float invL) {
 
 __device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
 
-__device__ __noinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
-    int fx, fy;
-    if (p.frozen) { fx = p.cix; fy = p.ciy; }
+// column of the atmosphere grid a tally goes to
+__device__ __forceinline__ void tally_col(const DevScene& S, const Photon& p, int& fx, int& fy) {
+    if (p.flags & FL_FROZEN) { fx = p.cix; fy = p.ciy; }
     else {
         fx = min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
         fy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
     }
-    const DevJob& J = S.jobs[p.job];
+}
+
+__device__ __noinline__ void flux_tally_at(const DevScene& S, int job, int fscale, float w, int fx, int fy, int var, int lev) {
+    const DevJob& J = S.jobs[job];
     const size_t nxy = size_t(S.nx) * S.ny;
     double sc = J.norm * double(nxy);
-    if (p.jflags & 2) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + lev);
-    tally_add(S.flux + ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx, double(p.w) * sc);
+    if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + lev);
+    tally_add(S.flux + ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx, double(w) * sc);
+}
+__device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
+    int fx, fy;
+    tally_col(S, p, fx, fy);
+    flux_tally_at(S, p.job, p.flags & FL_FSCALE, p.w, fx, fy, var, lev);
     CNT(CNT_TALLY)++;
 }
 
-__device__ __noinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
-    const int hx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-    const int hy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
-    const DevJob& J = S.jobs[p.job];
+__device__ __noinline__ void heat_tally_at(const DevScene& S, int job, int fscale, int fx, int fy, int iz, double dep) {
+    const DevJob& J = S.jobs[job];
     const size_t nxy = size_t(S.nx) * S.ny;
     double sc = J.norm * double(nxy);
-    if (p.jflags & 2) sc *= __ldg(S.job_fscale + size_t(p.job) * (S.nz + 1) + iz);
-    tally_add(S.heat + (size_t(J.slab) * S.nz + iz) * nxy + size_t(hy) * S.nx + hx, dep * sc);
+    if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + iz);
+    tally_add(S.heat + (size_t(J.slab) * S.nz + iz) * nxy + size_t(fy) * S.nx + fx, dep * sc);
+}
+__device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
+    int fx, fy;
+    tally_col(S, p, fx, fy);
+    heat_tally_at(S, p.job, p.flags & FL_FSCALE, fx, fy, iz, dep);
     CNT(CNT_TALLY)++;
 }
 
@@ -294,35 +347,33 @@ __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int 
 }
 
 // exact traversal toward a sensor: layer by layer, column by column inside the 3-D block (oblique views, sensors
-// inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.
-__device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p,
-                                             int fx, int fy, bool in3) {
-    const int has_abs = p.jflags & 1;
-    const float* ab = S.job_abs + size_t(p.job) * S.nz;
-    const int iz = p.iz;
+// inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.  Everything is passed by value so
+// that the photon never has to live in local memory.
+__device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __restrict__ smz, const float* __restrict__ sme1tot,
+                                             const DevSensor& se, float x, float y, float z, int iz, int job, int has_abs,
+                                             int frozen, int fx, int fy, bool in3, unsigned* n_visit_out) {
+    const float* ab = S.job_abs + size_t(job) * S.nz;
     const int nxy = S.nx * S.ny;
     unsigned n_visit = 0;
     float tau = 0.0f;
-    float x = p.x, y = p.y, z = p.z;
     int l = iz;
     const bool up = se.s.z > 0.0f;
-    if (up && z >= sm.z[l + 1] && l + 1 < S.nz) l++;
-    if (!up && z <= sm.z[l] && l > 0) l--;
-    bool have_col = in3 && (l == iz);
-    if (p.frozen) { fx = p.cix; fy = p.ciy; have_col = true; }
+    if (up && z >= smz[l + 1] && l + 1 < S.nz) l++;
+    if (!up && z <= smz[l] && l > 0) l--;
+    bool have_col = (in3 && (l == iz)) || frozen;
     const float isx = se.s.x != 0.0f ? 1.0f / se.s.x : RT_INF;
     const float isy = se.s.y != 0.0f ? 1.0f / se.s.y : RT_INF;
     const float isz = 1.0f / se.s.z;
     for (;;) {
-        const float zb = up ? fminf(sm.z[l + 1], se.zt) : fmaxf(sm.z[l], se.zt);
+        const float zb = up ? fminf(smz[l + 1], se.zt) : fmaxf(smz[l], se.zt);
         const float dl = fmaxf(0.0f, (zb - z) * isz);
-        const float base = sm.e1tot[l] + (has_abs ? __ldg(ab + l) : 0.0f);
+        const float base = sme1tot[l] + (has_abs ? __ldg(ab + l) : 0.0f);
         const bool l3 = (S.nz3 > 0) && l >= S.iz0 && l < S.iz0 + S.nz3;
         if (!l3) {
             tau += base * dl;
-            if (!p.frozen) { x = wrapf(x + se.s.x * dl, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * dl, S.Ly, S.inv_Ly); }
-            have_col = p.frozen;
-        } else if (p.frozen) {
+            if (!frozen) { x = wrapf(x + se.s.x * dl, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * dl, S.Ly, S.inv_Ly); }
+            have_col = frozen;
+        } else if (frozen) {
             tau += (base + __ldg(S.ext3tot + (l - S.iz0) * nxy + fy * S.nx + fx)) * dl;
             ++n_visit;
         } else {
@@ -356,7 +407,7 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, 
         if (up) { if (zb >= se.zt || l + 1 >= S.nz) break; l++; }
         else { if (zb <= se.zt || l == 0) break; l--; }
     }
-    CNT(CNT_VISIT) += n_visit;
+    *n_visit_out = n_visit;
     return tau;
 }
 
@@ -366,11 +417,12 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const Smem& sm, 
 __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, int fx, int fy,
                                         float s3) {
     const int iz = p.iz;
+    const bool frozen = (p.flags & FL_FROZEN) != 0;
     const bool in3 = (S.nz3 > 0) && iz >= S.iz0 && iz < S.iz0 + S.nz3;
-    if (se.fast_ok && se.s.z > 0.0f && (p.frozen || se.vertical_up)) {
+    if (se.fast_ok && se.s.z > 0.0f && (frozen || se.vertical_up)) {
         // ---- vertical (or column-frozen) fast path: O(1) look-ups in the precomputed tables
         float t1 = (sm.e1cum[se.lt] + sm.e1tot[se.lt] * (se.zt - sm.z[se.lt])) - (sm.e1cum[iz] + sm.e1tot[iz] * (p.z - sm.z[iz]));
-        if (p.jflags & 1) {
+        if (p.flags & FL_ABS) {
             const float* ab = S.job_abs + size_t(p.job) * S.nz;
             const float* cb = S.job_cabs + size_t(p.job) * (S.nz + 1);
             t1 += (__ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - sm.z[se.lt])) - (__ldg(cb + iz) + __ldg(ab + iz) * (p.z - sm.z[iz]));
@@ -378,8 +430,8 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
         if (S.nz3 > 0 && iz < S.iz0 + S.nz3) {
             const int nxy = S.nx * S.ny;
             if (!in3) {
-                fx = p.frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                fy = p.frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                fx = frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                fy = frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                 t1 += __ldg(S.tu3 + fy * S.nx + fx);
             } else {
                 t1 += __ldg(S.tu3 + (iz - S.iz0 + 1) * nxy + fy * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
@@ -388,7 +440,11 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
         }
         return fmaxf(0.0f, t1) * se.inv_sz;
     }
-    return le_tau_generic(S, sm, se, p, fx, fy, in3);
+    if (frozen) { fx = p.cix; fy = p.ciy; }
+    unsigned nv = 0;
+    const float t = le_tau_generic(S, sm.z, sm.e1tot, se, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
+    CNT(CNT_VISIT) += nv;
+    return t;
 }
 
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
@@ -397,7 +453,7 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
     const float tau = le_tau(S, sm, se, p, fx, fy, s3);
     const float contrib = fw * __expf(-tau) * se.inv_sz;
     int px, py;
-    if (p.frozen) {
+    if (p.flags & FL_FROZEN) {
         px = min(se.nxr - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(se.nxr)));
         py = min(se.nyr - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(se.nyr)));
     } else {
@@ -417,8 +473,10 @@ __device__ __forceinline__ float3 inv_dir(const float3 d) {
 }
 
 // sample the reflected direction `wo` at a surface of the given type; returns the weight factor (BRDF cos / pdf)
-__device__ __noinline__ float surface_sample(int sfc_type, const float* prm, const float3 wi, const float4 u, float3& wo) {
-    wo = make_float3(0.f, 0.f, 1.f);
+__device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, float p2, float p3, float p4, const float3 wi,
+                                             const float4 u, float3* wo_out) {
+    const float prm[5] = {p0, p1, p2, p3, p4};
+    float3 wo = make_float3(0.f, 0.f, 1.f);
     float fac = 0.0f;
     bool diffuse = true;
     if (sfc_type == B200RT_SFC_DSM && u.z >= prm[1]) diffuse = false;
@@ -444,25 +502,36 @@ __device__ __noinline__ float surface_sample(int sfc_type, const float* prm, con
             if (wo.z > 0.0f) fac = fresnel_unpol(cosg, prm[2], prm[3]) * cosg / (wi.z * n.z) * cm_shadow(wi.z, wo.z, sig2);
         }
     }
+    *wo_out = wo;
     return fac;
 }
 
-// Persistent-thread photon transport.  Every thread owns one photon at a time and regenerates it in place from a
-// global atomic counter (queue-based path regeneration).  To fight divergence the body runs in warp-convergent
-// PHASES, and a phase is only entered when enough lanes of the warp are waiting for it:
-//   (1) regeneration      when >= regen_min lanes are dead (or nothing is in flight),
-//   (2) flight            pure geometry on the two-level majorant grid (no RNG, no 3-D look-ups); lanes that reach a
-//                         tentative collision / the surface / TOA park, the loop ends when >= event_min lanes are parked,
-//   (3) tentative phase   Philox draw + voxel extinction look-up + null-collision rejection for all parked lanes,
-//   (4) event phase       shared by real collisions and surface hits: local estimates, new direction, roulette.
+// Persistent-thread photon transport with queue-based path regeneration.
+//
+// Every WARP owns a pool of NP photon slots in shared memory (NP = 2..4 x the warp width) and every slot is in one of
+// three queues: DEAD (waiting for regeneration), FLY (waiting for the flight phase) or EVENT (parked at a tentative
+// collision, the surface or TOA).  The warp repeatedly picks the FULLEST queue, loads up to 32 photons of it into
+// registers -- one per lane --, runs that phase convergently and writes the photons back with their new state:
+//   regeneration   next global photon indices from one 64-bit atomic counter (one atomicAdd per warp and phase),
+//                  Philox streams keyed by (job seed, global photon index): reproducible on any GPU count,
+//   flight         pure geometry on the two-level majorant grid (no RNG, no 3-D field look-ups); lanes that reach a
+//                  tentative collision / the surface / TOA park; ends when `event_min` lanes are parked,
+//   event          Philox draw + voxel extinction look-up + null-collision rejection for tentative collisions, then the
+//                  code shared by real collisions and surface hits: local estimates, new direction, roulette.
+// With NP >= 96 some queue always holds a full warp of work, so the phases run at (close to) 32 active lanes instead of
+// the ~11 a one-photon-per-lane loop reaches (profiles/README.md).  Nothing in the pool is shared between warps: the
+// only synchronisation is __syncwarp.
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
-template <bool PL, bool FZ>
-__global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant__ DevScene S) {
+template <bool PL, bool FZ, int NP>
+__global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
     Smem sm;
+    float* pool;
+    int* tag;
+    int* list;
     {
-        // 16-byte records first, then the double accumulators, then 4-byte tables
+        // 16-byte records first, then the double accumulators, then 4-byte tables, then the photon pools
         float4* q4 = smem_f4;
         float4* slabA = q4; q4 += S.nslab_z;
         int4* slabB = reinterpret_cast<int4*>(q4); q4 += S.nslab_z;
@@ -477,6 +546,10 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
         float* e1 = q; q += S.np1d * S.nz;
         float* o1 = q; q += S.np1d * S.nz;
         float* a1 = q; q += S.np1d * S.nz;
+        const int warp = threadIdx.x >> 5;
+        pool = q + size_t(warp) * (NFIELD * NP + NP + 32);
+        tag = reinterpret_cast<int*>(pool + NFIELD * NP);
+        list = tag + NP;
         for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
         for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
@@ -493,6 +566,7 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
         }
         for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
         for (int k = 0; k < 8; ++k) cnt[k * blockDim.x + threadIdx.x] = 0u;
+        for (int i = (threadIdx.x & 31); i < NP; i += 32) tag[i] = TAG_DEAD;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
         sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.cnt = cnt;
     }
@@ -500,222 +574,262 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const bool want_flux = PL && (S.target & B200RT_TARGET_FLUX) != 0;
     const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
     const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
     const int nxy = S.nx * S.ny;
+    constexpr int NG = NP / 32;
 
     unsigned n_cell = 0;
-    Photon p;
-    uint32_t rc0 = 0, rc1 = 0, rc2 = 0;   // Philox counter: photon index (lo, hi) and draw number
-    float3 invd = make_float3(0.f, 0.f, 0.f);
-    bool alive = false;
     bool exhausted = false;
-    bool stale = false;          // p.is may not be the fine slab of p.z (after sideways moves in empty coarse cells)
-    int ev = EV_NONE;
-    p.job = 0; p.jflags = 0; p.frozen = false;
 
 #define RNG4(out)                                                                                              \
     {                                                                                                          \
         const unsigned long long seed_ = S.jobs[p.job].seed;                                                   \
-        const uint4 r_ = philox4x32_10(rc0, rc1, rc2, 0xB200u, unsigned(seed_), unsigned(seed_ >> 32));        \
-        rc2++;                                                                                                 \
+        const uint4 r_ = philox4x32_10(p.rc0, p.rc1, p.rc2, 0xB200u, unsigned(seed_), unsigned(seed_ >> 32));  \
+        p.rc2++;                                                                                               \
         out = make_float4(u01(r_.x), u01(r_.y), u01(r_.z), u01(r_.w));                                          \
     }
 
     for (;;) {
-        // =========================================================== (1) regeneration (batched)
-        {
-            const bool need = !alive && !exhausted;
-            const unsigned mneed = __ballot_sync(FULL, need);
-            const unsigned malive = __ballot_sync(FULL, alive);
-            if (mneed != 0u && (__popc(mneed) >= S.regen_min || malive == 0u)) {
-                unsigned long long base = 0;
-                const int leader = __ffs(mneed) - 1;
-                if (lane == leader) base = atomicAdd(S.counter, (unsigned long long)__popc(mneed));
-                base = __shfl_sync(FULL, base, leader);
-                if (need) {
-                    const unsigned long long idx = base + __popc(mneed & ((1u << lane) - 1u));
-                    if (idx >= S.nphot_local) exhausted = true;
-                    else {
-                        int lo = 0, hi = S.njob - 1;
+        // =========================================================== pick the fullest queue
+        __syncwarp();
+        unsigned mF[NG], mE[NG];
+        int nF = 0, nE = 0;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const int t = tag[k * 32 + lane];
+            mF[k] = __ballot_sync(FULL, t == TAG_FLY);
+            mE[k] = __ballot_sync(FULL, t >= TAG_TENT);
+            nF += __popc(mF[k]); nE += __popc(mE[k]);
+        }
+        const int nD = exhausted ? 0 : NP - nF - nE;
+        if (nF == 0 && nE == 0 && nD == 0) break;
+        const int phase = (nE >= nF && nE >= nD) ? 2 : (nF >= nD ? 1 : 0);
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const unsigned m = phase == 2 ? mE[k] : (phase == 1 ? mF[k] : ~(mF[k] | mE[k]));
+            if ((m >> lane) & 1u) {
+                const int pos = n + __popc(m & lt_mask);
+                if (pos < 32) list[pos] = k * 32 + lane;
+            }
+            n += __popc(m);
+        }
+        n = min(n, 32);
+        __syncwarp();
+        const bool have = lane < n;
+        const int slot = have ? list[lane] : 0;
+
+        Photon p;
+        if (phase == 0) {
+            // ======================================================= regeneration
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)n);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned long long)n >= S.nphot_local) exhausted = true;
+            const unsigned long long idx = base + (unsigned long long)lane;
+            if (have && idx < S.nphot_local) {
+                int lo = 0, hi = S.njob - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+                }
+                p.job = lo;
+                const DevJob& J = S.jobs[lo];
+                p.flags = FL_DIRECT | (J.has_abs ? FL_ABS : 0) | (J.has_fscale ? FL_FSCALE : 0);
+                const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
+                p.rc0 = unsigned(gidx); p.rc1 = unsigned(gidx >> 32); p.rc2 = 0;
+                float4 u, v;
+                RNG4(u);
+                RNG4(v);
+                p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
+                if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
+                else p.d = S.src;
+                p.w = 1.0f; p.order = 0;
+                p.is = S.nslab_z - 1; p.iz = S.nz - 1;
+                p.za = p.z; p.iza = p.iz; p.leg = 0.0f; p.M = 0.0f;
+                p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
+                p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
+                if (FZ && S.solver == B200RT_SOLVER_IPA) {
+                    p.flags |= FL_FROZEN;
+                    p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
+                }
+                p.tau = -__logf(v.x);
+                CNT(CNT_PHOT)++;
+                if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
+                pool_store<NP>(pool, slot, p);
+                tag[slot] = TAG_FLY;
+            }
+            continue;
+        }
+
+        if (have) pool_load<NP>(pool, slot, p);
+
+        if (phase == 1) {
+            // ======================================================= flight: geometry only
+            const float3 invd = inv_dir(p.d);
+            int ev = EV_NONE;
+#pragma unroll 1
+            for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
+                if (have && ev == EV_NONE) {
+                    int is = p.is;
+                    float4 sa = sm.slabA[is];                   // zlo, zhi, 1-D majorant, fine z index in the majorant grid
+                    int4 sb = sm.slabB[is];                     // l0, l1, group
+                    const bool in3 = __float_as_int(sa.w) >= 0;
+                    const bool frozen = FZ && (p.flags & FL_FROZEN);
+                    // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
+                    float mj = 0.0f;
+                    if (in3) { mj = __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix); ++n_cell; }
+                    const int grp = sb.z;
+                    const bool empty = !in3 || mj < 0.0f;
+                    if (!PL && !empty && (p.flags & FL_STALE)) {
+                        // entered a non-empty coarse cell sideways: find the fine z slab of the current height
+                        const int4 gb = sm.grpB[grp];
+                        int lo = gb.x, hi = gb.y - 1;
                         while (lo < hi) {
                             const int mid = (lo + hi + 1) >> 1;
-                            if (S.jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+                            if (p.z >= sm.slabA[mid].x) lo = mid; else hi = mid - 1;
                         }
-                        p.job = lo;
-                        const DevJob& J = S.jobs[lo];
-                        p.jflags = J.has_abs | (J.has_fscale << 1);
-                        const unsigned long long gidx = (unsigned long long)S.shard_rank + (idx - J.first) * (unsigned long long)S.shard_world;
-                        rc0 = unsigned(gidx); rc1 = unsigned(gidx >> 32); rc2 = 0;
-                        float4 u, v;
-                        RNG4(u);
-                        RNG4(v);
-                        p.x = u.x * S.Lx; p.y = u.y * S.Ly; p.z = sm.z[S.nz];
-                        if (S.src_cos_half < 1.0f) p.d = rotate_dir(S.src, 1.0f - u.z * (1.0f - S.src_cos_half), RT_2PI * u.w);
-                        else p.d = S.src;
-                        p.w = 1.0f; p.order = 0; p.direct = true;
-                        p.is = S.nslab_z - 1; p.iz = S.nz - 1;
-                        p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
-                        p.frozen = FZ && (S.solver == B200RT_SOLVER_IPA);
-                        p.cix = min(S.ncx - 1, int(p.x * S.inv_Sx));
-                        p.ciy = min(S.ncy - 1, int(p.y * S.inv_Sy));
-                        if (FZ && p.frozen) { p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy; }
-                        p.tau = -__logf(v.x);
-                        invd = inv_dir(p.d);
-                        alive = true; stale = false; ev = EV_NONE;
-                        CNT(CNT_PHOT)++;
-                        if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
+                        is = lo; p.is = lo;
+                        sa = sm.slabA[is]; sb = sm.slabB[is];
+                        mj = fmaxf(0.0f, __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix));
                     }
-                }
-            }
-            if (__ballot_sync(FULL, alive) == 0u && __ballot_sync(FULL, !exhausted) == 0u) break;
-        }
-
-        // =========================================================== (2) flight: geometry only
-        float ev_M = 0.0f;
-        bool ev_in3 = false, ev_empty = false;
-#pragma unroll 1
-        for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
-            if (alive && ev == EV_NONE) {
-                int is = p.is;
-                float4 sa = sm.slabA[is];                   // zlo, zhi, 1-D majorant, fine z index in the majorant grid
-                int4 sb = sm.slabB[is];                     // l0, l1, group
-                const bool in3 = __float_as_int(sa.w) >= 0;
-                // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
-                float mj = 0.0f;
-                if (in3) { mj = __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix); ++n_cell; }
-                const int grp = sb.z;
-                const bool empty = !in3 || mj < 0.0f;
-                if (!PL && !empty && stale) {
-                    // entered a non-empty coarse cell sideways: find the fine z slab of the current height
-                    const int4 gb = sm.grpB[grp];
-                    int lo = gb.x, hi = gb.y - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (p.z >= sm.slabA[mid].x) lo = mid; else hi = mid - 1;
-                    }
-                    is = lo; p.is = lo;
-                    sa = sm.slabA[is]; sb = sm.slabB[is];
-                    mj = fmaxf(0.0f, __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix));
-                }
-                if (!empty) stale = false;
-                // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
-                float zlo, zhi, M;
-                int slo, shi, l0, l1;
-                if (empty) {
-                    const float4 ga = sm.grpA[grp];         // zlo, zhi, 1-D majorant of the group
-                    const int4 gb = sm.grpB[grp];
-                    zlo = ga.x; zhi = ga.y; M = ga.z;
-                    slo = gb.x; shi = gb.y; l0 = gb.z; l1 = gb.w;
-                } else {
-                    zlo = sa.x; zhi = sa.y;
-                    M = sa.z + mj;
-                    slo = is; shi = is + 1; l0 = sb.x; l1 = sb.y;
-                }
-                const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
-                const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
-                const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
-                // distances to the cell faces along the flight direction (branch-free)
-                const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
-                float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
-                if (p.d.z == 0.0f) tz = RT_INF;
-                float tx = RT_INF, ty = RT_INF;
-                if (in3 && !(FZ && p.frozen)) {
-                    tx = ((upx ? fminf(float(ixhi) * S.Sx, S.Lx) : float(ixlo) * S.Sx) - p.x) * invd.x;
-                    ty = ((upy ? fminf(float(iyhi) * S.Sy, S.Ly) : float(iylo) * S.Sy) - p.y) * invd.y;
-                    if (p.d.x == 0.0f) tx = RT_INF;
-                    if (p.d.y == 0.0f) ty = RT_INF;
-                }
-                tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
-                const float dexit = fminf(tz, fminf(tx, ty));
-                const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
-                const bool hit = dcol < dexit;
-                const float dmove = hit ? dcol : dexit;
-                const bool zcross = !hit && (tz <= tx) && (tz <= ty);
-                const bool xcross = !hit && !zcross && (tx <= ty);
-
-                // ---- move
-                float zn = p.z + p.d.z * dmove;
-                if (zcross) zn = upz ? zhi : zlo;
-                if (PL && (p.jflags & 1)) {
-                    // flux / heating targets: weight must be current at every level (cells are single layers here)
-                    const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + l0) * dmove);
-                    ACC(ACC_ATM) += double(p.w) - double(wn);
-                    if (want_heat) heat_tally(S, sm, p, l0, double(p.w) - double(wn));
-                    p.w = wn;
-                }
-                p.leg += dmove;
-                if (!(FZ && p.frozen)) {
-                    p.x += p.d.x * dmove; p.y += p.d.y * dmove;
-                    if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
-                }
-                p.z = zn;
-
-                if (hit) {
-                    // park at the tentative collision point; the RNG / look-up work is done in phase (3)
-                    ev = EV_TENT;
-                    ev_M = M; ev_in3 = in3; ev_empty = empty;
-                    p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
-                } else {
-                    p.tau = fmaxf(0.0f, p.tau - M * dexit);
-                    if (zcross) {
-                        stale = false;
-                        if (upz) {
-                            p.iz = l1 - 1;
-                            if (want_flux) flux_tally(S, sm, p, 2, l1);
-                            if (shi >= S.nslab_z) ev = EV_ESC;
-                            else { p.is = shi; p.iz = l1; }
-                        } else {
-                            p.iz = l0;
-                            if (want_flux) {
-                                if (p.direct) flux_tally(S, sm, p, 0, l0);
-                                flux_tally(S, sm, p, 1, l0);
-                            }
-                            if (slo == 0) ev = EV_SFC;
-                            else { p.is = slo - 1; p.iz = l0 - 1; }
-                        }
-                        if (ev == EV_NONE && !(FZ && p.frozen) && (!in3 || empty) && __float_as_int(sm.slabA[p.is].w) >= 0) {
-                            // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
-                            int cx = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
-                            int cy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
-                            if (in3) {   // stay inside the horizontal bounds of the coarse cell just traversed
-                                cx = min(min(S.ncx, ixhi) - 1, max(ixlo, cx));
-                                cy = min(min(S.ncy, iyhi) - 1, max(iylo, cy));
-                            }
-                            p.cix = cx; p.ciy = cy;
-                        }
+                    if (!empty) p.flags &= ~FL_STALE;
+                    // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
+                    float zlo, zhi, M;
+                    int slo, shi, l0, l1;
+                    if (empty) {
+                        const float4 ga = sm.grpA[grp];         // zlo, zhi, 1-D majorant of the group
+                        const int4 gb = sm.grpB[grp];
+                        zlo = ga.x; zhi = ga.y; M = ga.z;
+                        slo = gb.x; shi = gb.y; l0 = gb.z; l1 = gb.w;
                     } else {
-                        // sideways crossing (cyclic domain); branch-free selects
-                        const bool px = xcross;
-                        const bool up = px ? upx : upy;
-                        const int nc = px ? S.ncx : S.ncy;
-                        const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
-                        const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
-                        int ci = up ? ihi : ilo - 1;
-                        float pos = up ? float(ihi) * Sc : float(ilo) * Sc;
-                        if (ci >= nc) { ci = 0; pos = 0.0f; }
-                        if (ci < 0) { ci = nc - 1; pos = L; }
-                        if (px) { p.cix = ci; p.x = pos; } else { p.ciy = ci; p.y = pos; }
-                        if (empty) {
-                            // the other index follows the position inside the coarse cell that was crossed
-                            if (px) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
-                            else p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
-                            stale = (shi - slo > 1);
+                        zlo = sa.x; zhi = sa.y;
+                        M = sa.z + mj;
+                        slo = is; shi = is + 1; l0 = sb.x; l1 = sb.y;
+                    }
+                    const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
+                    const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
+                    const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
+                    // distances to the cell faces along the flight direction (branch-free)
+                    const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
+                    float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
+                    if (p.d.z == 0.0f) tz = RT_INF;
+                    float tx = RT_INF, ty = RT_INF;
+                    if (in3 && !frozen) {
+                        tx = ((upx ? fminf(float(ixhi) * S.Sx, S.Lx) : float(ixlo) * S.Sx) - p.x) * invd.x;
+                        ty = ((upy ? fminf(float(iyhi) * S.Sy, S.Ly) : float(iylo) * S.Sy) - p.y) * invd.y;
+                        if (p.d.x == 0.0f) tx = RT_INF;
+                        if (p.d.y == 0.0f) ty = RT_INF;
+                    }
+                    tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
+                    const float dexit = fminf(tz, fminf(tx, ty));
+                    const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
+                    const bool hit = dcol < dexit;
+                    const float dmove = hit ? dcol : dexit;
+                    const bool zcross = !hit && (tz <= tx) && (tz <= ty);
+                    const bool xcross = !hit && !zcross && (tx <= ty);
+
+                    // ---- move
+                    float zn = p.z + p.d.z * dmove;
+                    if (zcross) zn = upz ? zhi : zlo;
+                    if (PL && (p.flags & FL_ABS)) {
+                        // flux / heating targets: weight must be current at every level (cells are single layers here)
+                        const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + l0) * dmove);
+                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        if (want_heat) heat_tally(S, sm, p, l0, double(p.w) - double(wn));
+                        p.w = wn;
+                    }
+                    p.leg += dmove;
+                    if (!frozen) {
+                        p.x += p.d.x * dmove; p.y += p.d.y * dmove;
+                        if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
+                    }
+                    p.z = zn;
+
+                    if (hit) {
+                        // park at the tentative collision point; the RNG / look-up work is done in the event phase
+                        ev = EV_TENT;
+                        p.M = M;
+                        p.flags = (p.flags & ~(FL_IN3 | FL_EMPTY)) | (in3 ? FL_IN3 : 0) | (empty ? FL_EMPTY : 0);
+                        p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
+                    } else {
+                        p.tau = fmaxf(0.0f, p.tau - M * dexit);
+                        if (zcross) {
+                            p.flags &= ~FL_STALE;
+                            if (upz) {
+                                p.iz = l1 - 1;
+                                if (want_flux) flux_tally(S, sm, p, 2, l1);
+                                if (shi >= S.nslab_z) ev = EV_ESC;
+                                else { p.is = shi; p.iz = l1; }
+                            } else {
+                                p.iz = l0;
+                                if (want_flux) {
+                                    if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, l0);
+                                    flux_tally(S, sm, p, 1, l0);
+                                }
+                                if (slo == 0) ev = EV_SFC;
+                                else { p.is = slo - 1; p.iz = l0 - 1; }
+                            }
+                            if (ev == EV_NONE && !frozen && (!in3 || empty) && __float_as_int(sm.slabA[p.is].w) >= 0) {
+                                // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
+                                int cx = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
+                                int cy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
+                                if (in3) {   // stay inside the horizontal bounds of the coarse cell just traversed
+                                    cx = min(min(S.ncx, ixhi) - 1, max(ixlo, cx));
+                                    cy = min(min(S.ncy, iyhi) - 1, max(iylo, cy));
+                                }
+                                p.cix = cx; p.ciy = cy;
+                            }
+                        } else {
+                            // sideways crossing (cyclic domain); branch-free selects
+                            const bool px = xcross;
+                            const bool up = px ? upx : upy;
+                            const int nc = px ? S.ncx : S.ncy;
+                            const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
+                            const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
+                            int ci = up ? ihi : ilo - 1;
+                            float pos = up ? float(ihi) * Sc : float(ilo) * Sc;
+                            if (ci >= nc) { ci = 0; pos = 0.0f; }
+                            if (ci < 0) { ci = nc - 1; pos = L; }
+                            if (px) { p.cix = ci; p.x = pos; } else { p.ciy = ci; p.y = pos; }
+                            if (empty) {
+                                // the other index follows the position inside the coarse cell that was crossed
+                                if (px) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
+                                else p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
+                                if (shi - slo > 1) p.flags |= FL_STALE; else p.flags &= ~FL_STALE;
+                            }
                         }
                     }
                 }
+                const unsigned flying = __ballot_sync(FULL, have && ev == EV_NONE);
+                if (flying == 0u || n - __popc(flying) >= S.event_min) break;
             }
-            const unsigned parked = __ballot_sync(FULL, alive && ev != EV_NONE);
-            const unsigned flying = __ballot_sync(FULL, alive && ev == EV_NONE);
-            if (__popc(parked) >= S.event_min || flying == 0u) break;
+            if (have) {
+                pool_store<NP>(pool, slot, p);
+                tag[slot] = ev == EV_NONE ? TAG_FLY : (ev == EV_TENT ? TAG_TENT : (ev == EV_SFC ? TAG_SFC : TAG_ESC));
+            }
+            continue;
         }
 
-        // =========================================================== (3) tentative collisions: accept or reject
+        // =========================================================== event phase
+        int ev = EV_NONE;
+        bool alive = have;
+        if (have) {
+            const int t = tag[slot];
+            ev = t == TAG_TENT ? EV_TENT : (t == TAG_SFC ? EV_SFC : EV_ESC);
+        }
+        // ---- tentative collisions: accept or reject
         float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
         float ev_s3 = 0.0f, ev_uc = 0.0f;
         int ev_fx = 0, ev_fy = 0, ev_vox = 0;
-        if (alive && ev == EV_TENT) {
+        bool ev_in3 = false;
+        if (ev == EV_TENT) {
+            const bool frozen = FZ && (p.flags & FL_FROZEN);
+            const bool ev_empty = (p.flags & FL_EMPTY) != 0;
+            ev_in3 = (p.flags & FL_IN3) != 0;
             float4 u;
             RNG4(u);
             const int izn = p.iz;
@@ -723,7 +837,7 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
             float s3 = 0.0f;
             int fx = 0, fy = 0, vox = 0;
             if (ev_in3) {
-                if (FZ && p.frozen) { fx = p.cix; fy = p.ciy; }
+                if (frozen) { fx = p.cix; fy = p.ciy; }
                 else {
                     const int shx = ev_empty ? S.shx : 0, shy = ev_empty ? S.shy : 0;
                     const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
@@ -735,32 +849,32 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                 if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT(CNT_TENT)++; }
             }
             p.tau = -__logf(u.y);
-            const float uc = u.x * ev_M;
+            const float uc = u.x * p.M;
             if (uc < sig) {
                 ev = EV_COLL;
                 ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox;
-                if (ev_in3 && ev_empty && !(FZ && p.frozen)) {
+                if (ev_in3 && ev_empty && !frozen) {
                     // keep the fine cell indices consistent with the position inside the coarse cell
                     p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
                 }
             } else ev = EV_NONE;
         }
 
-        // =========================================================== (4) events
-        if (alive && ev != EV_NONE) {
+        // ---- events (real collisions, surface hits, escapes)
+        if (ev != EV_NONE) do {
             const int evk = ev;
-            ev = EV_NONE;
-            // ---- path-integrated gas absorption of the leg that ends here
+            const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
+            // path-integrated gas absorption of the leg that ends here
             const int izb = (evk == EV_SFC) ? 0 : (evk == EV_ESC ? S.nz - 1 : p.iz);
-            if (evk == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; stale = false; }
-            if (!PL && (p.jflags & 1)) {
-                const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, fabsf(invd.z));
+            if (evk == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; p.flags &= ~FL_STALE; }
+            if (!PL && (p.flags & FL_ABS)) {
+                const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, inv_absdz);
                 const float wn = p.w * __expf(-ta);
                 ACC(ACC_ATM) += double(p.w) - double(wn);
                 p.w = wn;
             }
             p.za = p.z; p.iza = izb; p.leg = 0.0f;
-            if (evk == EV_ESC) { ACC(ACC_TOA) += double(p.w); alive = false; continue; }
+            if (evk == EV_ESC) { ACC(ACC_TOA) += double(p.w); alive = false; break; }
 
             float4 u;
             float3 newd;
@@ -768,7 +882,7 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
             int fx = 0, fy = 0;
             float s3 = 0.0f;
             int sfc_type = 0;
-            float prm[5];
+            float prm[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
             if (evk == EV_COLL) {
                 // ---- real collision: pick the scattering component (uc is uniform on [0, sig))
@@ -810,20 +924,21 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                     if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
                 }
                 p.w = wn;
-                p.order++; p.direct = false;
-                if (!(p.w > 0.0f)) { alive = false; continue; }
-                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                p.order++; p.flags &= ~FL_DIRECT;
+                if (!(p.w > 0.0f)) { alive = false; break; }
+                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !(p.flags & FL_FROZEN)) {
                     if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
                     else { p.cix = fx; p.ciy = fy; }
                     p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                    p.frozen = true;
+                    p.flags |= FL_FROZEN;
                 }
             } else {
                 // ---- surface hit
                 CNT(CNT_SFC)++;
                 RNG4(u);
+                const bool frozen = FZ && (p.flags & FL_FROZEN);
                 int sx, sy;
-                if (FZ && p.frozen) {
+                if (frozen) {
                     sx = min(S.sfc_nx - 1, int((float(p.cix) + 0.5f) / float(S.nx) * float(S.sfc_nx)));
                     sy = min(S.sfc_ny - 1, int((float(p.ciy) + 0.5f) / float(S.ny) * float(S.sfc_ny)));
                 } else {
@@ -835,8 +950,8 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
 #pragma unroll
                 for (int q = 0; q < 5; ++q) prm[q] = __ldg(S.sfc_param + q * sn + si);
                 if (want_rad && S.nz3 > 0 && S.iz0 == 0) {
-                    fx = (FZ && p.frozen) ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-                    fy = (FZ && p.frozen) ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+                    fx = frozen ? p.cix : min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+                    fy = frozen ? p.ciy : min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                     s3 = __ldg(S.ext3tot + fy * S.nx + fx);
                 }
             }
@@ -852,7 +967,7 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                         const float cosang = p.d.x * se.s.x + p.d.y * se.s.y + p.d.z * se.s.z;
                         f = phase_eval(S.pt, apf, cosang) * (0.25f / RT_PI);
                     } else {
-                        f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm, wi, se.s) * se.s.z : 0.0f;
+                        f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, se.s) * se.s.z : 0.0f;
                     }
                     if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3);
                 }
@@ -864,30 +979,29 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                 if (apf >= 1.0f) { float4 v; RNG4(v); xi_tab = v.x; }
                 const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
                 newd = rotate_dir(p.d, mu, RT_2PI * u.w);
-                if (p.order >= S.iso_max) { ACC(ACC_RR) -= double(p.w); alive = false; continue; }
+                if (p.order >= S.iso_max) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
             } else {
                 float3 wo;
-                const float fac = surface_sample(sfc_type, prm, wi, u, wo);
+                const float fac = surface_sample(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, u, &wo);
                 const float wn = p.w * fac;
                 ACC(ACC_SFC) += double(p.w) - double(wn);
                 p.w = wn;
-                if (!(p.w > 0.0f)) { alive = false; continue; }
+                if (!(p.w > 0.0f)) { alive = false; break; }
                 const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
                 newd = make_float3(wo.x * nrm, wo.y * nrm, wo.z * nrm);
-                p.direct = false; p.order++;
+                p.flags &= ~FL_DIRECT; p.order++;
             }
             p.d = newd;
-            invd = inv_dir(p.d);
             if (evk == EV_SFC) {
                 if (want_flux) flux_tally(S, sm, p, 2, 0);
-                if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && p.frozen)) {
+                if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && (p.flags & FL_FROZEN))) {
                     p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                     p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
                 }
-                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !p.frozen) {
+                if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !(p.flags & FL_FROZEN)) {
                     p.cix = min(S.nx - 1, max(0, int(p.x * S.inv_dx))); p.ciy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
                     p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
-                    p.frozen = true;
+                    p.flags |= FL_FROZEN;
                 }
             }
             // ---- Russian roulette (Pho_wmin / Pho_wfac), shared
@@ -895,9 +1009,14 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
                 float xi = u.w;
                 if (evk == EV_COLL) { float4 v; RNG4(v); xi = v.x; }
                 if (xi * S.wfac < p.w) { ACC(ACC_RR) += double(S.wfac) - double(p.w); p.w = S.wfac; }
-                else { ACC(ACC_RR) -= double(p.w); CNT(CNT_KILL)++; alive = false; continue; }
+                else { ACC(ACC_RR) -= double(p.w); CNT(CNT_KILL)++; alive = false; break; }
             }
-            if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; continue; }
+            if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
+        } while (0);
+
+        if (have) {
+            if (alive) pool_store<NP>(pool, slot, p);
+            tag[slot] = alive ? TAG_FLY : TAG_DEAD;
         }
     }
 #undef RNG4
@@ -930,9 +1049,18 @@ __global__ void __launch_bounds__(256, 3) transport_kernel(const __grid_constant
 #undef CNT
 
 typedef void (*transport_fn)(const DevScene);
-static transport_fn pick_transport(bool pl, bool fz) {
-    if (pl) return fz ? transport_kernel<true, true> : transport_kernel<true, false>;
-    return fz ? transport_kernel<false, true> : transport_kernel<false, false>;
+template <int NP>
+static transport_fn pick_transport_np(bool pl, bool fz) {
+    if (pl) return fz ? transport_kernel<true, true, NP> : transport_kernel<true, false, NP>;
+    return fz ? transport_kernel<false, true, NP> : transport_kernel<false, false, NP>;
+}
+static transport_fn pick_transport(bool pl, bool fz, int np) {
+    switch (np) {
+        case 32: return pick_transport_np<32>(pl, fz);
+        case 64: return pick_transport_np<64>(pl, fz);
+        case 128: return pick_transport_np<128>(pl, fz);
+        default: return pick_transport_np<96>(pl, fz);
+    }
 }
 
 // ============================================================================ test-hook kernels
@@ -958,7 +1086,7 @@ __global__ void brdf_eval_kernel(int type, const float* prm5, const double* din,
     for (int q = 0; q < 5; ++q) p[q] = prm5[q];
     const float3 wi = make_float3(-float(din[3 * i]), -float(din[3 * i + 1]), -float(din[3 * i + 2]));
     const float3 wo = make_float3(float(dout[3 * i]), float(dout[3 * i + 1]), float(dout[3 * i + 2]));
-    f[i] = double(brdf_eval(type, p, wi, wo));
+    f[i] = double(brdf_eval(type, p[0], p[1], p[2], p[3], p[4], wi, wo));
 }
 
 // ============================================================================ host side
@@ -978,6 +1106,7 @@ struct Handle {
     b200rt_options opt{};
     int numSM = 0;
     size_t smem_bytes = 0, smem_tables = 0;
+    int pool_slots = 0;
     bool k_pl = false, k_fz = false;
     // owned device memory
     std::vector<DevBuf*> pool;
@@ -1138,7 +1267,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.solver = opt->solver; S.target = opt->target;
     S.wmin = float(opt->wmin); S.wfac = float(opt->wfac > 0 ? opt->wfac : 1.0);
     S.iso_ss = opt->iso_ss > 0 ? opt->iso_ss : 1;
-    S.iso_max = opt->iso_max > 0 ? opt->iso_max : 1000000;
+    S.iso_max = opt->iso_max > 0 ? std::min(opt->iso_max, (1 << 24) - 1) : 1000000;
     S.shard_rank = opt->shard_rank; S.shard_world = opt->shard_world;
 
     // ------------------------------------------------ super-voxel grid
@@ -1162,7 +1291,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     int cmz = opt->cmz > 0 ? opt->cmz : 5;
     if (per_level) { shx = 0; shy = 0; cmz = 1; }
     S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 16;
-    S.event_min = opt->event_min > 0 ? opt->event_min : 20;
+    S.event_min = opt->event_min > 0 ? opt->event_min : 12;
     S.regen_min = opt->regen_min > 0 ? opt->regen_min : 8;
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
@@ -1239,7 +1368,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.slab_lay0 = (const int*)H->slab_lay0.p; S.slab_cz = (const int*)H->slab_cz.p; S.slab_maj1d = (const float*)H->slab_maj1d.p;
     H->smem_tables = 16 * (2 * size_t(S.nslab_z) + 2 * size_t(S.ngroup)) + sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz);
     H->smem_bytes = H->smem_tables + 256 * (4 * 8 + 8 * 4);
-    if (H->smem_bytes > 200 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
+    if (H->smem_bytes > 120 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
+    if (S.ncx > 65535 || S.ncy > 65535 || nz > 65535) return fail(H, B200RT_ERR_ARG, "grid too large for the packed photon record (65535 cells per axis)");
 
     // ------------------------------------------------ 3-D block
     if (nz3 > 0) {
@@ -1390,8 +1520,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
 
     H->k_pl = per_level; H->k_fz = (opt->solver != B200RT_SOLVER_3D);
-    if (H->smem_bytes > 48 * 1024)
-        CK(cudaFuncSetAttribute(pick_transport(H->k_pl, H->k_fz), cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->smem_bytes)));
+    H->pool_slots = opt->pool_slots;
+    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 96 && H->pool_slots != 128)
+        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 32, 64, 96 or 128");
     H->opt = *opt;
     H->have_scene = true;
     H->ran = false;
@@ -1403,6 +1534,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     if (!H) return B200RT_ERR_ARG;
     if (!H->have_scene) return fail(H, B200RT_ERR_STATE, "b200rt_run called before b200rt_upload_scene");
     if (!jobs || njob < 1) return fail(H, B200RT_ERR_ARG, "no jobs");
+    if (njob > 65535) return fail(H, B200RT_ERR_ARG, "at most 65535 jobs per run");
     CK(cudaSetDevice(H->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     DevScene& S = H->S;
@@ -1457,11 +1589,15 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     CK(cudaMemsetAsync(H->counter.p, 0, 16, st));
     CK(cudaMemsetAsync(H->stats.p, 0, sizeof(DevStats), st));
 
+    // launch shape: the per-warp photon pools decide how many blocks fit on an SM (shared memory), see DESIGN.md
     int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : 256;
     tpb = std::min(256, std::max(32, (tpb / 32) * 32));
+    const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz);
-    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4);
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, np);
+    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * (size_t(NFIELD) * np + np + 32) * 4;
+    if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));
     if (bps < 1) return fail(H, B200RT_ERR_CUDA, "transport kernel does not fit on an SM");
     if (H->opt.blocks_per_sm > 0) bps = std::min(bps, H->opt.blocks_per_sm);

@@ -221,8 +221,9 @@ __device__ __forceinline__ float lsrt_kernel_sum(const float* p, const float3 wi
     const float v = p[0] + p[1] * kgeo + p[2] * kvol;
     return v > 0.0f ? v : 0.0f;
 }
-__device__ __noinline__ float brdf_eval(int type, const float* p, const float3 wi, const float3 wo) {
+__device__ __noinline__ float brdf_eval(int type, float p0, float p1, float p2, float p3, float p4, const float3 wi, const float3 wo) {
     if (wi.z <= 0.0f || wo.z <= 0.0f) return 0.0f;
+    const float p[5] = {p0, p1, p2, p3, p4};
     if (type == 2) return p[1] * p[0] * (1.0f / RT_PI) + (1.0f - p[1]) * dsm_spec_brdf(p, wi, wo);
     if (type == 4) return lsrt_kernel_sum(p, wi, wo) * (1.0f / RT_PI);
     return p[0] * (1.0f / RT_PI);

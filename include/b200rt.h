@@ -127,10 +127,10 @@ typedef struct b200rt_options {
     int32_t shard_world;          /*   i % shard_world == shard_rank  (1 GPU: 0 / 1)           */
     int32_t svx, svy, svz;        /* fine majorant cell in voxels / layers; 0 = auto           */
     int32_t cmx, cmy, cmz;        /* coarse (empty-space) cell in fine cells (x, y: power of two); 0 = auto */
-    int32_t flight_steps;         /* max cell crossings per lane between two event phases; 0 = auto */
-    int32_t event_min;            /* lanes waiting for an event that end the flight loop early; 0 = auto */
-    int32_t regen_min;            /* dead lanes of a warp that trigger a regeneration; 0 = auto */
-    int32_t _pad;
+    int32_t flight_steps;         /* max cell crossings per lane in one flight phase; 0 = auto      */
+    int32_t event_min;            /* lanes parked at an event that end a flight phase early; 0 = auto */
+    int32_t regen_min;            /* reserved (was: dead lanes of a warp that trigger a regeneration) */
+    int32_t pool_slots;           /* photon slots per warp in shared memory: 32, 64, 96, 128; 0 = auto */
     int32_t iso_ss;               /* Pho_iso_SS: partial-3D switches to 1-D after this order   */
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */
     int32_t threads_per_block;    /* 0 = auto                                                  */
