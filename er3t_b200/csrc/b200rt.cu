@@ -244,8 +244,8 @@ enum { FL_DIRECT = 1, FL_FROZEN = 2, FL_STALE = 4, FL_ABS = 8, FL_FSCALE = 16, F
 
 // pool record: NFIELD 32-bit words per slot, structure-of-arrays ([field][slot]) so that lanes touch distinct banks
 enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_JOB, F_ZA, F_LEG, F_RC0, F_RC1, F_RC2, F_M, NFIELD };
-// slot states.  FLY: waiting for the flight phase; TENT / SFC / ESC: parked at an event, waiting for the event phase
-enum { TAG_DEAD = 0, TAG_FLY = 1, TAG_TENT = 2, TAG_SFC = 3, TAG_ESC = 4 };
+// 32-bit words of shared memory per warp: the pool + three queues (DEAD, FLY, EVENT) of 16-bit slot numbers
+#define POOL_WORDS(np) (NFIELD * (np) + 3 * (np) / 2)
 enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3, EV_TENT = 4 };
 
 template <int NP>
@@ -277,6 +277,44 @@ __device__ __forceinline__ void pool_store(float* __restrict__ f, int s, const P
     f[F_ZA * NP + s] = p.za; f[F_LEG * NP + s] = p.leg;
     f[F_RC0 * NP + s] = __uint_as_float(p.rc0); f[F_RC1 * NP + s] = __uint_as_float(p.rc1); f[F_RC2 * NP + s] = __uint_as_float(p.rc2);
     f[F_M * NP + s] = p.M;
+}
+
+// the flight phase reads and writes only the geometric part of the record
+template <int NP, bool PL>
+__device__ __forceinline__ void pool_load_flight(const float* __restrict__ f, int s, Photon& p) {
+    p.x = f[F_X * NP + s]; p.y = f[F_Y * NP + s]; p.z = f[F_Z * NP + s];
+    p.d.x = f[F_DX * NP + s]; p.d.y = f[F_DY * NP + s]; p.d.z = f[F_DZ * NP + s];
+    p.tau = f[F_TAU * NP + s];
+    const unsigned c = __float_as_uint(f[F_CELL * NP + s]);
+    p.cix = int(c & 0xffffu); p.ciy = int(c >> 16);
+    const unsigned l = __float_as_uint(f[F_LAY * NP + s]);
+    p.is = int(l & 0xffffu); p.iz = int(l >> 16);
+    const unsigned o = __float_as_uint(f[F_ORD * NP + s]);
+    p.flags = int(o & 0xffu); p.order = int(o >> 8);
+    p.leg = f[F_LEG * NP + s];
+    p.M = 0.0f;
+    if (PL) {
+        p.w = f[F_W * NP + s];
+        p.job = int(__float_as_uint(f[F_JOB * NP + s]) & 0xffffu);
+    }
+}
+template <int NP, bool PL>
+__device__ __forceinline__ void pool_store_flight(float* __restrict__ f, int s, const Photon& p) {
+    f[F_X * NP + s] = p.x; f[F_Y * NP + s] = p.y; f[F_Z * NP + s] = p.z;
+    f[F_TAU * NP + s] = p.tau;
+    f[F_CELL * NP + s] = __uint_as_float(unsigned(p.cix) | (unsigned(p.ciy) << 16));
+    f[F_LAY * NP + s] = __uint_as_float(unsigned(p.is) | (unsigned(p.iz) << 16));
+    f[F_ORD * NP + s] = __uint_as_float(unsigned(p.flags) | (unsigned(p.order) << 8));
+    f[F_LEG * NP + s] = p.leg;
+    f[F_M * NP + s] = p.M;
+    if (PL) f[F_W * NP + s] = p.w;
+}
+// a rejected (null) collision changes the optical-depth budget, the draw counter and the layer only
+template <int NP>
+__device__ __forceinline__ void pool_store_reject(float* __restrict__ f, int s, const Photon& p) {
+    f[F_TAU * NP + s] = p.tau;
+    f[F_RC2 * NP + s] = __uint_as_float(p.rc2);
+    f[F_LAY * NP + s] = __uint_as_float(unsigned(p.is) | (unsigned(p.iz) << 16));
 }
 
 __device__ __forceinline__ float wrapf(float x, float L, float invL) {
@@ -528,8 +566,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
     extern __shared__ float4 smem_f4[];
     Smem sm;
     float* pool;
-    int* tag;
-    int* list;
+    unsigned short *qD, *qF, *qE;
     {
         // 16-byte records first, then the double accumulators, then 4-byte tables, then the photon pools
         float4* q4 = smem_f4;
@@ -547,9 +584,10 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         float* o1 = q; q += S.np1d * S.nz;
         float* a1 = q; q += S.np1d * S.nz;
         const int warp = threadIdx.x >> 5;
-        pool = q + size_t(warp) * (NFIELD * NP + NP + 32);
-        tag = reinterpret_cast<int*>(pool + NFIELD * NP);
-        list = tag + NP;
+        pool = q + size_t(warp) * POOL_WORDS(NP);
+        qD = reinterpret_cast<unsigned short*>(pool + NFIELD * NP);
+        qF = qD + NP;
+        qE = qF + NP;
         for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
         for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
@@ -566,7 +604,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         }
         for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
         for (int k = 0; k < 8; ++k) cnt[k * blockDim.x + threadIdx.x] = 0u;
-        for (int i = (threadIdx.x & 31); i < NP; i += 32) tag[i] = TAG_DEAD;
+        for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
         sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.cnt = cnt;
     }
@@ -579,10 +617,11 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
     const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
     const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
     const int nxy = S.nx * S.ny;
-    constexpr int NG = NP / 32;
 
     unsigned n_cell = 0;
     bool exhausted = false;
+    // queue lengths (warp-uniform): DEAD slots, FLY slots, EVENT slots.  Queues are LIFO stacks of slot numbers.
+    int nD = NP, nF = 0, nE = 0;
 
 #define RNG4(out)                                                                                              \
     {                                                                                                          \
@@ -591,46 +630,35 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         p.rc2++;                                                                                               \
         out = make_float4(u01(r_.x), u01(r_.y), u01(r_.z), u01(r_.w));                                          \
     }
+// push the slots of the lanes for which `cond` holds onto queue `q` (length `cnt`); `val` is the queue entry
+#define QPUSH(q, cnt, cond, val)                                              \
+    {                                                                         \
+        const unsigned m_ = __ballot_sync(FULL, (cond));                      \
+        if (cond) (q)[(cnt) + __popc(m_ & lt_mask)] = (unsigned short)(val);   \
+        (cnt) += __popc(m_);                                                  \
+    }
 
     for (;;) {
         // =========================================================== pick the fullest queue
         __syncwarp();
-        unsigned mF[NG], mE[NG];
-        int nF = 0, nE = 0;
-#pragma unroll
-        for (int k = 0; k < NG; ++k) {
-            const int t = tag[k * 32 + lane];
-            mF[k] = __ballot_sync(FULL, t == TAG_FLY);
-            mE[k] = __ballot_sync(FULL, t >= TAG_TENT);
-            nF += __popc(mF[k]); nE += __popc(mE[k]);
-        }
-        const int nD = exhausted ? 0 : NP - nF - nE;
-        if (nF == 0 && nE == 0 && nD == 0) break;
-        const int phase = (nE >= nF && nE >= nD) ? 2 : (nF >= nD ? 1 : 0);
-        int n = 0;
-#pragma unroll
-        for (int k = 0; k < NG; ++k) {
-            const unsigned m = phase == 2 ? mE[k] : (phase == 1 ? mF[k] : ~(mF[k] | mE[k]));
-            if ((m >> lane) & 1u) {
-                const int pos = n + __popc(m & lt_mask);
-                if (pos < 32) list[pos] = k * 32 + lane;
-            }
-            n += __popc(m);
-        }
-        n = min(n, 32);
-        __syncwarp();
-        const bool have = lane < n;
-        const int slot = have ? list[lane] : 0;
+        const int nDe = exhausted ? 0 : nD;
+        if (nF == 0 && nE == 0 && nDe == 0) break;
+        const int phase = (nE >= nF && nE >= nDe) ? 2 : (nF >= nDe ? 1 : 0);
 
         Photon p;
         if (phase == 0) {
             // ======================================================= regeneration
+            const int n = min(nD, 32);
+            const bool have = lane < n;
+            const int slot = have ? int(qD[nD - 1 - lane]) : 0;
+            nD -= n;
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)n);
             base = __shfl_sync(FULL, base, 0);
             if (base + (unsigned long long)n >= S.nphot_local) exhausted = true;
             const unsigned long long idx = base + (unsigned long long)lane;
-            if (have && idx < S.nphot_local) {
+            const bool born = have && idx < S.nphot_local;
+            if (born) {
                 int lo = 0, hi = S.njob - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
@@ -660,16 +688,22 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                 CNT(CNT_PHOT)++;
                 if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
                 pool_store<NP>(pool, slot, p);
-                tag[slot] = TAG_FLY;
             }
+            QPUSH(qF, nF, born, slot);
+            QPUSH(qD, nD, have && !born, slot);
             continue;
         }
 
-        if (have) pool_load<NP>(pool, slot, p);
-
         if (phase == 1) {
             // ======================================================= flight: geometry only
+            const int n = min(nF, 32);
+            const bool have = lane < n;
+            const int slot = have ? int(qF[nF - 1 - lane]) : 0;
+            nF -= n;
+            if (have) pool_load_flight<NP, PL>(pool, slot, p);
             const float3 invd = inv_dir(p.d);
+            const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
+            const bool frozen = FZ && (p.flags & FL_FROZEN);
             int ev = EV_NONE;
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
@@ -678,7 +712,6 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     float4 sa = sm.slabA[is];                   // zlo, zhi, 1-D majorant, fine z index in the majorant grid
                     int4 sb = sm.slabB[is];                     // l0, l1, group
                     const bool in3 = __float_as_int(sa.w) >= 0;
-                    const bool frozen = FZ && (p.flags & FL_FROZEN);
                     // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
                     float mj = 0.0f;
                     if (in3) { mj = __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix); ++n_cell; }
@@ -696,7 +729,6 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                         sa = sm.slabA[is]; sb = sm.slabB[is];
                         mj = fmaxf(0.0f, __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix));
                     }
-                    if (!empty) p.flags &= ~FL_STALE;
                     // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
                     float zlo, zhi, M;
                     int slo, shi, l0, l1;
@@ -714,7 +746,6 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
                     const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
                     // distances to the cell faces along the flight direction (branch-free)
-                    const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
                     float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
                     if (p.d.z == 0.0f) tz = RT_INF;
                     float tx = RT_INF, ty = RT_INF;
@@ -749,78 +780,85 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     }
                     p.z = zn;
 
+                    // ---- book-keeping, one instruction stream for all three outcomes (hit / vertical / sideways)
+                    int fl = p.flags & ~FL_STALE;
+                    if (empty && (p.flags & FL_STALE)) fl |= FL_STALE;                   // only a non-empty cell resolves staleness
                     if (hit) {
-                        // park at the tentative collision point; the RNG / look-up work is done in the event phase
+                        // park at the tentative collision point; RNG, voxel look-up and the layer search happen in the
+                        // event phase
                         ev = EV_TENT;
                         p.M = M;
-                        p.flags = (p.flags & ~(FL_IN3 | FL_EMPTY)) | (in3 ? FL_IN3 : 0) | (empty ? FL_EMPTY : 0);
-                        p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, zn) : l0;
+                        fl = (fl & ~(FL_IN3 | FL_EMPTY)) | (in3 ? FL_IN3 : 0) | (empty ? FL_EMPTY : 0);
                     } else {
                         p.tau = fmaxf(0.0f, p.tau - M * dexit);
+                        // sideways candidates (selects; discarded when the crossing is vertical)
+                        const bool px = xcross;
+                        const bool upc = px ? upx : upy;
+                        const int nc = px ? S.ncx : S.ncy;
+                        const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
+                        const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
+                        int ci = upc ? ihi : ilo - 1;
+                        float pos = float(upc ? ihi : ilo) * Sc;
+                        if (ci >= nc) { ci = 0; pos = 0.0f; }
+                        if (ci < 0) { ci = nc - 1; pos = L; }
+                        // vertical candidates
+                        const int nis = upz ? shi : slo - 1;
+                        const bool out = upz ? (shi >= S.nslab_z) : (slo == 0);
+                        bool new3 = in3;                                                 // is the next cell inside the 3-D block?
                         if (zcross) {
-                            p.flags &= ~FL_STALE;
-                            if (upz) {
-                                p.iz = l1 - 1;
-                                if (want_flux) flux_tally(S, sm, p, 2, l1);
-                                if (shi >= S.nslab_z) ev = EV_ESC;
-                                else { p.is = shi; p.iz = l1; }
-                            } else {
-                                p.iz = l0;
-                                if (want_flux) {
+                            fl &= ~FL_STALE;
+                            if (PL && want_flux) {
+                                p.iz = upz ? l1 - 1 : l0;
+                                if (upz) flux_tally(S, sm, p, 2, l1);
+                                else {
                                     if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, l0);
                                     flux_tally(S, sm, p, 1, l0);
                                 }
-                                if (slo == 0) ev = EV_SFC;
-                                else { p.is = slo - 1; p.iz = l0 - 1; }
                             }
-                            if (ev == EV_NONE && !frozen && (!in3 || empty) && __float_as_int(sm.slabA[p.is].w) >= 0) {
-                                // entering the 3-D block, or leaving an empty coarse cell vertically: locate the fine cell
-                                int cx = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
-                                int cy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
-                                if (in3) {   // stay inside the horizontal bounds of the coarse cell just traversed
-                                    cx = min(min(S.ncx, ixhi) - 1, max(ixlo, cx));
-                                    cy = min(min(S.ncy, iyhi) - 1, max(iylo, cy));
-                                }
-                                p.cix = cx; p.ciy = cy;
+                            if (out) { ev = upz ? EV_ESC : EV_SFC; new3 = false; }
+                            else {
+                                p.is = nis; p.iz = upz ? l1 : l0 - 1;
+                                new3 = __float_as_int(sm.slabA[nis].w) >= 0;
                             }
                         } else {
-                            // sideways crossing (cyclic domain); branch-free selects
-                            const bool px = xcross;
-                            const bool up = px ? upx : upy;
-                            const int nc = px ? S.ncx : S.ncy;
-                            const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
-                            const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
-                            int ci = up ? ihi : ilo - 1;
-                            float pos = up ? float(ihi) * Sc : float(ilo) * Sc;
-                            if (ci >= nc) { ci = 0; pos = 0.0f; }
-                            if (ci < 0) { ci = nc - 1; pos = L; }
                             if (px) { p.cix = ci; p.x = pos; } else { p.ciy = ci; p.y = pos; }
-                            if (empty) {
-                                // the other index follows the position inside the coarse cell that was crossed
-                                if (px) p.ciy = min(min(S.ncy, iyhi) - 1, max(iylo, int(p.y * S.inv_Sy)));
-                                else p.cix = min(min(S.ncx, ixhi) - 1, max(ixlo, int(p.x * S.inv_Sx)));
-                                if (shi - slo > 1) p.flags |= FL_STALE; else p.flags &= ~FL_STALE;
-                            }
+                            if (empty && shi - slo > 1) fl |= FL_STALE;
+                        }
+                        // the fine cell indices follow the position after a move through anything larger than a fine cell
+                        // (1-D region or empty coarse cell); the index of an axis just crossed sideways stays explicit
+                        if (!frozen && new3 && (empty || !in3)) {
+                            const int bxlo = in3 ? ixlo : 0, bxhi = in3 ? min(S.ncx, ixhi) : S.ncx;
+                            const int bylo = in3 ? iylo : 0, byhi = in3 ? min(S.ncy, iyhi) : S.ncy;
+                            const int cx = min(bxhi - 1, max(bxlo, int(p.x * S.inv_Sx)));
+                            const int cy = min(byhi - 1, max(bylo, int(p.y * S.inv_Sy)));
+                            if (zcross || !px) p.cix = cx;
+                            if (zcross || px) p.ciy = cy;
                         }
                     }
+                    p.flags = fl;
                 }
                 const unsigned flying = __ballot_sync(FULL, have && ev == EV_NONE);
                 if (flying == 0u || n - __popc(flying) >= S.event_min) break;
             }
-            if (have) {
-                pool_store<NP>(pool, slot, p);
-                tag[slot] = ev == EV_NONE ? TAG_FLY : (ev == EV_TENT ? TAG_TENT : (ev == EV_SFC ? TAG_SFC : TAG_ESC));
-            }
+            if (have) pool_store_flight<NP, PL>(pool, slot, p);
+            QPUSH(qF, nF, have && ev == EV_NONE, slot);
+            QPUSH(qE, nE, have && ev != EV_NONE, slot | (ev << 8));
             continue;
         }
 
         // =========================================================== event phase
+        const int n = min(nE, 32);
+        const bool have = lane < n;
         int ev = EV_NONE;
-        bool alive = have;
+        int slot = 0;
         if (have) {
-            const int t = tag[slot];
-            ev = t == TAG_TENT ? EV_TENT : (t == TAG_SFC ? EV_SFC : EV_ESC);
+            const int e = int(qE[nE - 1 - lane]);
+            slot = e & 255; ev = e >> 8;
         }
+        nE -= n;
+        if (have) pool_load<NP>(pool, slot, p);
+        bool alive = have;
+        bool rejected = false;
         // ---- tentative collisions: accept or reject
         float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
         float ev_s3 = 0.0f, ev_uc = 0.0f;
@@ -832,6 +870,13 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
             ev_in3 = (p.flags & FL_IN3) != 0;
             float4 u;
             RNG4(u);
+            {
+                // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
+                const int4 sb = sm.slabB[p.is];
+                int l0 = sb.x, l1 = sb.y;
+                if (ev_empty) { const int4 gb = sm.grpB[sb.z]; l0 = gb.z; l1 = gb.w; }
+                p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, p.z) : l0;
+            }
             const int izn = p.iz;
             float sig = sm.e1tot[izn];
             float s3 = 0.0f;
@@ -857,7 +902,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     // keep the fine cell indices consistent with the position inside the coarse cell
                     p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
                 }
-            } else ev = EV_NONE;
+            } else { ev = EV_NONE; rejected = true; }
         }
 
         // ---- events (real collisions, surface hits, escapes)
@@ -1014,12 +1059,14 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
             if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
         } while (0);
 
-        if (have) {
-            if (alive) pool_store<NP>(pool, slot, p);
-            tag[slot] = alive ? TAG_FLY : TAG_DEAD;
+        if (have && alive) {
+            if (rejected) pool_store_reject<NP>(pool, slot, p); else pool_store<NP>(pool, slot, p);
         }
+        QPUSH(qF, nF, have && alive, slot);
+        QPUSH(qD, nD, have && !alive, slot);
     }
 #undef RNG4
+#undef QPUSH
 
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
     unsigned long long c[9] = {CNT(CNT_PHOT), n_cell, CNT(CNT_TENT), CNT(CNT_COLL), CNT(CNT_SFC), CNT(CNT_LE), CNT(CNT_VISIT),
@@ -1595,7 +1642,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, np);
-    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * (size_t(NFIELD) * np + np + 32) * 4;
+    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4;
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));
