@@ -62,6 +62,7 @@ struct DevScene {
     float dx, dy, Lx, Ly, inv_dx, inv_dy, inv_Lx, inv_Ly;
     int svx, svy, svz, ncx, ncy, ncz;
     float Sx, Sy, inv_Sx, inv_Sy;
+    float Lux, Luy;           // domain size in units of fine cells (nx / svx, ny / svy; the last cell may be partial)
     int nslab_z;
     int ngroup;               // coarse z groups of fine slabs
     int nCx, nCy, shx, shy;   // coarse (emptiness) grid: 2^shx x 2^shy fine cells per coarse cell
@@ -210,9 +211,9 @@ struct Smem {
     const float* o1;
     const float* a1;
     // packed per-cell records: one 16-byte shared-memory load each instead of a chain of dependent look-ups
-    const float4* slabA;  // [nslab_z]   (zlo, zhi, 1-D majorant, bits: fine z index in the majorant grid or -1)
+    const float4* slabA;  // [nslab_z]   (zlo, zhi, 1-D majorant, bits: fine z index in the majorant grid | group << 16; sign bit: 1-D slab)
     const int4* slabB;    // [nslab_z]   (first layer, one-past-last layer, coarse group, -)
-    const float4* grpA;   // [ngroup]    (zlo, zhi, 1-D majorant, bits: coarse z index in the emptiness grid or -1)
+    const float4* grpA;   // [ngroup]    (zlo, zhi, 1-D majorant, bits: first fine slab | one-past-last fine slab << 16)
     const int4* grpB;     // [ngroup]    (first fine slab, one-past-last fine slab, first layer, one-past-last layer)
     double* acc;          // per-thread energy accumulators [4][blockDim]: toa, sfc, atm, roulette
     unsigned* cnt;        // per-thread event counters [8][blockDim]
@@ -248,9 +249,12 @@ enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_
 #define POOL_WORDS(np) (NFIELD * (np) + 3 * (np) / 2)
 enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3, EV_TENT = 4 };
 
+// The pool keeps the horizontal position in units of fine majorant cells (what the flight phase works in); the event
+// and regeneration phases convert to metres on load and back on store.  Both happen at fixed points of a photon's
+// history, so a trajectory does not depend on which other photons share its warp (reproducibility).
 template <int NP>
-__device__ __forceinline__ void pool_load(const float* __restrict__ f, int s, Photon& p) {
-    p.x = f[F_X * NP + s]; p.y = f[F_Y * NP + s]; p.z = f[F_Z * NP + s];
+__device__ __forceinline__ void pool_load(const float* __restrict__ f, int s, Photon& p, float Sx, float Sy) {
+    p.x = f[F_X * NP + s] * Sx; p.y = f[F_Y * NP + s] * Sy; p.z = f[F_Z * NP + s];
     p.d.x = f[F_DX * NP + s]; p.d.y = f[F_DY * NP + s]; p.d.z = f[F_DZ * NP + s];
     p.w = f[F_W * NP + s]; p.tau = f[F_TAU * NP + s];
     const unsigned c = __float_as_uint(f[F_CELL * NP + s]);
@@ -266,8 +270,8 @@ __device__ __forceinline__ void pool_load(const float* __restrict__ f, int s, Ph
     p.M = f[F_M * NP + s];
 }
 template <int NP>
-__device__ __forceinline__ void pool_store(float* __restrict__ f, int s, const Photon& p) {
-    f[F_X * NP + s] = p.x; f[F_Y * NP + s] = p.y; f[F_Z * NP + s] = p.z;
+__device__ __forceinline__ void pool_store(float* __restrict__ f, int s, const Photon& p, float inv_Sx, float inv_Sy) {
+    f[F_X * NP + s] = p.x * inv_Sx; f[F_Y * NP + s] = p.y * inv_Sy; f[F_Z * NP + s] = p.z;
     f[F_DX * NP + s] = p.d.x; f[F_DY * NP + s] = p.d.y; f[F_DZ * NP + s] = p.d.z;
     f[F_W * NP + s] = p.w; f[F_TAU * NP + s] = p.tau;
     f[F_CELL * NP + s] = __uint_as_float(unsigned(p.cix) | (unsigned(p.ciy) << 16));
@@ -593,13 +597,15 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
         for (int i = threadIdx.x; i < S.nslab_z; i += blockDim.x) {
             const int l0 = S.slab_lay0[i], l1 = S.slab_lay0[i + 1];
-            slabA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.slab_maj1d[i], __int_as_float(S.slab_cz[i]));
+            const int cz = S.slab_cz[i];
+            const int w = cz >= 0 ? (cz | (S.slab_cg[i] << 16)) : int(0x80000000u | (unsigned(S.slab_cg[i]) << 16));
+            slabA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.slab_maj1d[i], __int_as_float(w));
             slabB[i] = make_int4(l0, l1, S.slab_cg[i], 0);
         }
         for (int i = threadIdx.x; i < S.ngroup; i += blockDim.x) {
             const int s0 = S.group_lo[i], s1 = S.group_lo[i + 1];
             const int l0 = S.slab_lay0[s0], l1 = S.slab_lay0[s1];
-            grpA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.group_maj1d[i], __int_as_float(S.group_cz[i]));
+            grpA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.group_maj1d[i], __int_as_float(int(unsigned(s0) | (unsigned(s1) << 16))));
             grpB[i] = make_int4(s0, s1, l0, l1);
         }
         for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
@@ -687,7 +693,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                 p.tau = -__logf(v.x);
                 CNT(CNT_PHOT)++;
                 if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
-                pool_store<NP>(pool, slot, p);
+                pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
             QPUSH(qF, nF, born, slot);
             QPUSH(qD, nD, have && !born, slot);
@@ -696,151 +702,134 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
 
         if (phase == 1) {
             // ======================================================= flight: geometry only
+            // Horizontal position in units of fine majorant cells (ux, uy): faces are integers, so a face distance is one
+            // int->float conversion, one subtraction and one multiplication.  1-D slabs behave like one empty coarse
+            // cell that spans the whole domain: the periodic wrap is an ordinary face crossing.  One branch-free
+            // instruction stream serves fine cells, empty coarse cells and 1-D slab groups.
             const int n = min(nF, 32);
             const bool have = lane < n;
             const int slot = have ? int(qF[nF - 1 - lane]) : 0;
             nF -= n;
             if (have) pool_load_flight<NP, PL>(pool, slot, p);
-            const float3 invd = inv_dir(p.d);
-            const bool upz = p.d.z > 0.0f, upx = p.d.x > 0.0f, upy = p.d.y > 0.0f;
             const bool frozen = FZ && (p.flags & FL_FROZEN);
+            // direction per fine cell; zero components are replaced by a tiny value (no special cases in the loop)
+            float dux = frozen ? 0.0f : p.d.x * S.inv_Sx, duy = frozen ? 0.0f : p.d.y * S.inv_Sy, dzg = p.d.z;
+            if (fabsf(dux) < 1e-20f) dux = 1e-20f;
+            if (fabsf(duy) < 1e-20f) duy = 1e-20f;
+            if (fabsf(dzg) < 1e-12f) dzg = 1e-12f;
+            const float kx = 1.0f / dux, ky = 1.0f / duy, kz = 1.0f / dzg;
+            const bool upz = dzg > 0.0f;
+            const int ox = dux > 0.0f ? 1 : 0, oy = duy > 0.0f ? 1 : 0;
+            const int upmx = -ox, upmy = -oy;
+            float ux = p.x, uy = p.y;                                  // cell units in the pool
+            const float Lux = S.Lux, Luy = S.Luy;
+            const int ncx = S.ncx, ncy = S.ncy;
+            const int cmx = (1 << S.shx) - 1, cmy = (1 << S.shy) - 1;
+            const float* __restrict__ majp = S.maj;
             int ev = EV_NONE;
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
                 if (have && ev == EV_NONE) {
-                    int is = p.is;
-                    float4 sa = sm.slabA[is];                   // zlo, zhi, 1-D majorant, fine z index in the majorant grid
-                    int4 sb = sm.slabB[is];                     // l0, l1, group
-                    const bool in3 = __float_as_int(sa.w) >= 0;
+                    float4 A = sm.slabA[p.is];                  // zlo, zhi, 1-D majorant, bits: cz | group << 16 (< 0: 1-D slab)
+                    int aw = __float_as_int(A.w);
+                    bool in3 = aw >= 0;
                     // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
-                    float mj = 0.0f;
-                    if (in3) { mj = __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix); ++n_cell; }
-                    const int grp = sb.z;
-                    const bool empty = !in3 || mj < 0.0f;
-                    if (!PL && !empty && (p.flags & FL_STALE)) {
+                    float mj = -1.0f;
+                    if (in3) { mj = __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix); ++n_cell; }
+                    if (!PL && mj >= 0.0f && (p.flags & FL_STALE)) {
                         // entered a non-empty coarse cell sideways: find the fine z slab of the current height
-                        const int4 gb = sm.grpB[grp];
-                        int lo = gb.x, hi = gb.y - 1;
+                        const int gw = __float_as_int(sm.grpA[(aw >> 16) & 0x7fff].w);
+                        int lo = gw & 0xffff, hi = int(unsigned(gw) >> 16) - 1;
                         while (lo < hi) {
                             const int mid = (lo + hi + 1) >> 1;
                             if (p.z >= sm.slabA[mid].x) lo = mid; else hi = mid - 1;
                         }
-                        is = lo; p.is = lo;
-                        sa = sm.slabA[is]; sb = sm.slabB[is];
-                        mj = fmaxf(0.0f, __ldg(S.maj + (__float_as_int(sa.w) * S.ncy + p.ciy) * S.ncx + p.cix));
+                        p.is = lo;
+                        A = sm.slabA[lo]; aw = __float_as_int(A.w);
+                        mj = fmaxf(0.0f, __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix));
                     }
-                    // cell = whole coarse cell when it holds no 3-D extinction, else the fine majorant cell
-                    float zlo, zhi, M;
-                    int slo, shi, l0, l1;
-                    if (empty) {
-                        const float4 ga = sm.grpA[grp];         // zlo, zhi, 1-D majorant of the group
-                        const int4 gb = sm.grpB[grp];
-                        zlo = ga.x; zhi = ga.y; M = ga.z;
-                        slo = gb.x; shi = gb.y; l0 = gb.z; l1 = gb.w;
-                    } else {
-                        zlo = sa.x; zhi = sa.y;
-                        M = sa.z + mj;
-                        slo = is; shi = is + 1; l0 = sb.x; l1 = sb.y;
-                    }
-                    const int shx = empty ? S.shx : 0, shy = empty ? S.shy : 0;
-                    const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
-                    const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
-                    // distances to the cell faces along the flight direction (branch-free)
-                    float tz = ((upz ? zhi : zlo) - p.z) * invd.z;
-                    if (p.d.z == 0.0f) tz = RT_INF;
-                    float tx = RT_INF, ty = RT_INF;
-                    if (in3 && !frozen) {
-                        tx = ((upx ? fminf(float(ixhi) * S.Sx, S.Lx) : float(ixlo) * S.Sx) - p.x) * invd.x;
-                        ty = ((upy ? fminf(float(iyhi) * S.Sy, S.Ly) : float(iylo) * S.Sy) - p.y) * invd.y;
-                        if (p.d.x == 0.0f) tx = RT_INF;
-                        if (p.d.y == 0.0f) ty = RT_INF;
-                    }
-                    tz = fmaxf(tz, 0.0f); tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
-                    const float dexit = fminf(tz, fminf(tx, ty));
-                    const float dcol = M > 0.0f ? __fdividef(p.tau, M) : RT_INF;
-                    const bool hit = dcol < dexit;
-                    const float dmove = hit ? dcol : dexit;
-                    const bool zcross = !hit && (tz <= tx) && (tz <= ty);
-                    const bool xcross = !hit && !zcross && (tx <= ty);
+                    const float4 G = sm.grpA[(aw >> 16) & 0x7fff];    // zlo, zhi, 1-D majorant of the group, bits: slo | shi << 16
+                    const bool empty = mj < 0.0f;                       // 1-D slabs count as empty
+                    // box in cell units: the fine cell, the enclosing coarse cell, or the whole domain (1-D slabs)
+                    const int mx = in3 ? (empty ? cmx : 0) : 0x3fffffff, my = in3 ? (empty ? cmy : 0) : 0x3fffffff;
+                    const int bxlo = p.cix & ~mx, bylo = p.ciy & ~my;
+                    const int fxi = bxlo + ((mx + 1) & upmx), fyi = bylo + ((my + 1) & upmy);    // face index ahead
+                    const float fxf = fminf(float(fxi), Lux), fyf = fminf(float(fyi), Luy);
+                    const float zf = upz ? (empty ? G.y : A.y) : (empty ? G.x : A.x);
+                    const float tx = (fxf - ux) * kx, ty = (fyf - uy) * ky, tz = (zf - p.z) * kz;
+                    const float M = empty ? G.z : A.z + mj;
+                    const float dexit = fmaxf(0.0f, fminf(tz, fminf(tx, ty)));
+                    const bool hit = p.tau < M * dexit;
+                    const float dmove = hit ? __fdividef(p.tau, M) : dexit;
+                    const bool zc = !hit && (tz <= tx) && (tz <= ty);
+                    const bool xc = !hit && !zc && (tx <= ty);
+                    const bool yc = !hit && !zc && !xc;
 
                     // ---- move
-                    float zn = p.z + p.d.z * dmove;
-                    if (zcross) zn = upz ? zhi : zlo;
                     if (PL && (p.flags & FL_ABS)) {
-                        // flux / heating targets: weight must be current at every level (cells are single layers here)
-                        const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + l0) * dmove);
+                        // flux / heating targets: weight must be current at every level (slabs are single layers here)
+                        const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
                         ACC(ACC_ATM) += double(p.w) - double(wn);
-                        if (want_heat) heat_tally(S, sm, p, l0, double(p.w) - double(wn));
+                        if (want_heat) {
+                            p.x = ux * S.Sx; p.y = uy * S.Sy;
+                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
+                        }
                         p.w = wn;
                     }
                     p.leg += dmove;
-                    if (!frozen) {
-                        p.x += p.d.x * dmove; p.y += p.d.y * dmove;
-                        if (!in3) { p.x = wrapf(p.x, S.Lx, S.inv_Lx); p.y = wrapf(p.y, S.Ly, S.inv_Ly); }
-                    }
-                    p.z = zn;
+                    p.z = zc ? zf : p.z + dzg * dmove;
+                    ux += dux * dmove; uy += duy * dmove;
+                    p.tau = fmaxf(0.0f, p.tau - M * dmove);
 
-                    // ---- book-keeping, one instruction stream for all three outcomes (hit / vertical / sideways)
-                    int fl = p.flags & ~FL_STALE;
-                    if (empty && (p.flags & FL_STALE)) fl |= FL_STALE;                   // only a non-empty cell resolves staleness
+                    // ---- new cell: indices follow the position inside the box just traversed; the axis that was
+                    //      crossed is set explicitly (periodic wrap included)
+                    int cxn = fxi - 1 + ox, cyn = fyi - 1 + oy;
+                    float uxn = fxf, uyn = fyf;
+                    if (fxi >= ncx) { cxn = 0; uxn = 0.0f; }
+                    if (cxn < 0) { cxn = ncx - 1; uxn = Lux; }
+                    if (fyi >= ncy) { cyn = 0; uyn = 0.0f; }
+                    if (cyn < 0) { cyn = ncy - 1; uyn = Luy; }
+                    const int cxi = min(min(p.cix | mx, ncx - 1), max(bxlo, __float2int_rd(ux)));
+                    const int cyi = min(min(p.ciy | my, ncy - 1), max(bylo, __float2int_rd(uy)));
+                    p.cix = xc ? cxn : cxi; ux = xc ? uxn : ux;
+                    p.ciy = yc ? cyn : cyi; uy = yc ? uyn : uy;
+
+                    const int gw = __float_as_int(G.w);
+                    const int slo = empty ? (gw & 0xffff) : p.is, shi = empty ? int(unsigned(gw) >> 16) : p.is + 1;
+                    int fl = p.flags;
+                    if (mj >= 0.0f) fl &= ~FL_STALE;                              // only a non-empty cell resolves staleness
+                    if ((xc || yc) && shi - slo > 1) fl |= FL_STALE;
                     if (hit) {
                         // park at the tentative collision point; RNG, voxel look-up and the layer search happen in the
                         // event phase
                         ev = EV_TENT;
                         p.M = M;
                         fl = (fl & ~(FL_IN3 | FL_EMPTY)) | (in3 ? FL_IN3 : 0) | (empty ? FL_EMPTY : 0);
-                    } else {
-                        p.tau = fmaxf(0.0f, p.tau - M * dexit);
-                        // sideways candidates (selects; discarded when the crossing is vertical)
-                        const bool px = xcross;
-                        const bool upc = px ? upx : upy;
-                        const int nc = px ? S.ncx : S.ncy;
-                        const int ilo = px ? ixlo : iylo, ihi = px ? ixhi : iyhi;
-                        const float Sc = px ? S.Sx : S.Sy, L = px ? S.Lx : S.Ly;
-                        int ci = upc ? ihi : ilo - 1;
-                        float pos = float(upc ? ihi : ilo) * Sc;
-                        if (ci >= nc) { ci = 0; pos = 0.0f; }
-                        if (ci < 0) { ci = nc - 1; pos = L; }
-                        // vertical candidates
-                        const int nis = upz ? shi : slo - 1;
-                        const bool out = upz ? (shi >= S.nslab_z) : (slo == 0);
-                        bool new3 = in3;                                                 // is the next cell inside the 3-D block?
-                        if (zcross) {
-                            fl &= ~FL_STALE;
-                            if (PL && want_flux) {
-                                p.iz = upz ? l1 - 1 : l0;
-                                if (upz) flux_tally(S, sm, p, 2, l1);
-                                else {
-                                    if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, l0);
-                                    flux_tally(S, sm, p, 1, l0);
-                                }
-                            }
-                            if (out) { ev = upz ? EV_ESC : EV_SFC; new3 = false; }
+                    }
+                    if (zc) {
+                        fl &= ~FL_STALE;
+                        if (PL && want_flux) {
+                            p.x = ux * S.Sx; p.y = uy * S.Sy;
+                            if (upz) flux_tally(S, sm, p, 2, p.is + 1);
                             else {
-                                p.is = nis; p.iz = upz ? l1 : l0 - 1;
-                                new3 = __float_as_int(sm.slabA[nis].w) >= 0;
+                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is);
+                                flux_tally(S, sm, p, 1, p.is);
                             }
-                        } else {
-                            if (px) { p.cix = ci; p.x = pos; } else { p.ciy = ci; p.y = pos; }
-                            if (empty && shi - slo > 1) fl |= FL_STALE;
                         }
-                        // the fine cell indices follow the position after a move through anything larger than a fine cell
-                        // (1-D region or empty coarse cell); the index of an axis just crossed sideways stays explicit
-                        if (!frozen && new3 && (empty || !in3)) {
-                            const int bxlo = in3 ? ixlo : 0, bxhi = in3 ? min(S.ncx, ixhi) : S.ncx;
-                            const int bylo = in3 ? iylo : 0, byhi = in3 ? min(S.ncy, iyhi) : S.ncy;
-                            const int cx = min(bxhi - 1, max(bxlo, int(p.x * S.inv_Sx)));
-                            const int cy = min(byhi - 1, max(bylo, int(p.y * S.inv_Sy)));
-                            if (zcross || !px) p.cix = cx;
-                            if (zcross || px) p.ciy = cy;
-                        }
+                        const int nis = upz ? shi : slo - 1;
+                        if (nis >= S.nslab_z) ev = EV_ESC;
+                        else if (nis < 0) ev = EV_SFC;
+                        else p.is = nis;
                     }
                     p.flags = fl;
                 }
                 const unsigned flying = __ballot_sync(FULL, have && ev == EV_NONE);
                 if (flying == 0u || n - __popc(flying) >= S.event_min) break;
             }
-            if (have) pool_store_flight<NP, PL>(pool, slot, p);
+            if (have) {
+                p.x = ux; p.y = uy;
+                pool_store_flight<NP, PL>(pool, slot, p);
+            }
             QPUSH(qF, nF, have && ev == EV_NONE, slot);
             QPUSH(qE, nE, have && ev != EV_NONE, slot | (ev << 8));
             continue;
@@ -856,7 +845,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
             slot = e & 255; ev = e >> 8;
         }
         nE -= n;
-        if (have) pool_load<NP>(pool, slot, p);
+        if (have) pool_load<NP>(pool, slot, p, S.Sx, S.Sy);
         bool alive = have;
         bool rejected = false;
         // ---- tentative collisions: accept or reject
@@ -1060,7 +1049,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         } while (0);
 
         if (have && alive) {
-            if (rejected) pool_store_reject<NP>(pool, slot, p); else pool_store<NP>(pool, slot, p);
+            if (rejected) pool_store_reject<NP>(pool, slot, p); else pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
         }
         QPUSH(qF, nF, have && alive, slot);
         QPUSH(qD, nD, have && !alive, slot);
@@ -1345,6 +1334,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
     S.Sx = float(sc->dx * svx); S.Sy = float(sc->dy * svy); S.inv_Sx = 1.0f / S.Sx; S.inv_Sy = 1.0f / S.Sy;
     S.inv_Lx = 1.0f / S.Lx; S.inv_Ly = 1.0f / S.Ly;
+    S.Lux = float(double(sc->nx) / svx); S.Luy = float(double(sc->ny) / svy);
     S.shx = shx; S.shy = shy;
     S.nCx = (S.ncx + (1 << shx) - 1) >> shx; S.nCy = (S.ncy + (1 << shy) - 1) >> shy;
 
@@ -1416,7 +1406,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     H->smem_tables = 16 * (2 * size_t(S.nslab_z) + 2 * size_t(S.ngroup)) + sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz);
     H->smem_bytes = H->smem_tables + 256 * (4 * 8 + 8 * 4);
     if (H->smem_bytes > 120 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
-    if (S.ncx > 65535 || S.ncy > 65535 || nz > 65535) return fail(H, B200RT_ERR_ARG, "grid too large for the packed photon record (65535 cells per axis)");
+    if (S.ncx > 65535 || S.ncy > 65535 || nz > 65535 || S.ncz > 65535 || S.ngroup > 32767)
+        return fail(H, B200RT_ERR_ARG, "grid too large for the packed photon record (65535 cells per axis)");
 
     // ------------------------------------------------ 3-D block
     if (nz3 > 0) {
