@@ -244,9 +244,10 @@ struct Photon {
 enum { FL_DIRECT = 1, FL_FROZEN = 2, FL_STALE = 4, FL_ABS = 8, FL_FSCALE = 16, FL_IN3 = 32, FL_EMPTY = 64 };
 
 // pool record: NFIELD 32-bit words per slot, structure-of-arrays ([field][slot]) so that lanes touch distinct banks
-enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_JOB, F_ZA, F_LEG, F_RC0, F_RC1, F_RC2, F_M, NFIELD };
-// 32-bit words of shared memory per warp: the pool + three queues (DEAD, FLY, EVENT) of 16-bit slot numbers
-#define POOL_WORDS(np) (NFIELD * (np) + 3 * (np) / 2)
+enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_JOB, F_ZA, F_LEG, F_RC0, F_RC1, F_RC2, F_M, F_AUX, NFIELD };
+// 32-bit words of shared memory per warp: the pool + five queues (DEAD, FLY, TENTATIVE, COLLISION, SURFACE) of 16-bit
+// slot numbers
+#define POOL_WORDS(np) (NFIELD * (np) + 5 * (np) / 2)
 enum { EV_NONE = 0, EV_COLL = 1, EV_SFC = 2, EV_ESC = 3, EV_TENT = 4 };
 
 // The pool keeps the horizontal position in units of fine majorant cells (what the flight phase works in); the event
@@ -319,6 +320,19 @@ __device__ __forceinline__ void pool_store_reject(float* __restrict__ f, int s, 
     f[F_TAU * NP + s] = p.tau;
     f[F_RC2 * NP + s] = __uint_as_float(p.rc2);
     f[F_LAY * NP + s] = __uint_as_float(unsigned(p.is) | (unsigned(p.iz) << 16));
+}
+
+// an accepted collision hands over to the collision phase: new weight / order / cell / layer, the next optical-depth
+// budget and draw counter, plus (in fields the finished leg no longer needs) the phase-function code, the two random
+// numbers of the scattering direction and the 3-D extinction of the voxel
+template <int NP>
+__device__ __forceinline__ void pool_store_accept(float* __restrict__ f, int s, const Photon& p, float apf, float uz, float uw, float s3) {
+    f[F_W * NP + s] = p.w; f[F_TAU * NP + s] = p.tau;
+    f[F_RC2 * NP + s] = __uint_as_float(p.rc2);
+    f[F_CELL * NP + s] = __uint_as_float(unsigned(p.cix) | (unsigned(p.ciy) << 16));
+    f[F_LAY * NP + s] = __uint_as_float(unsigned(p.is) | (unsigned(p.iz) << 16));
+    f[F_ORD * NP + s] = __uint_as_float(unsigned(p.flags) | (unsigned(p.order) << 8));
+    f[F_LEG * NP + s] = apf; f[F_ZA * NP + s] = uz; f[F_AUX * NP + s] = uw; f[F_M * NP + s] = s3;
 }
 
 __device__ __forceinline__ float wrapf(float x, float L, float invL) {
@@ -570,7 +584,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
     extern __shared__ float4 smem_f4[];
     Smem sm;
     float* pool;
-    unsigned short *qD, *qF, *qE;
+    unsigned short *qD, *qF, *qE, *qC, *qS;
     {
         // 16-byte records first, then the double accumulators, then 4-byte tables, then the photon pools
         float4* q4 = smem_f4;
@@ -592,6 +606,8 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         qD = reinterpret_cast<unsigned short*>(pool + NFIELD * NP);
         qF = qD + NP;
         qE = qF + NP;
+        qC = qE + NP;
+        qS = qC + NP;
         for (int i = threadIdx.x; i <= S.nz; i += blockDim.x) { z[i] = S.zgrd[i]; e1cum[i] = S.e1cum[i]; }
         for (int i = threadIdx.x; i < S.nz; i += blockDim.x) e1tot[i] = S.e1tot[i];
         for (int i = threadIdx.x; i < S.np1d * S.nz; i += blockDim.x) { e1[i] = S.e1[i]; o1[i] = S.o1[i]; a1[i] = S.a1[i]; }
@@ -626,8 +642,8 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
 
     unsigned n_cell = 0;
     bool exhausted = false;
-    // queue lengths (warp-uniform): DEAD slots, FLY slots, EVENT slots.  Queues are LIFO stacks of slot numbers.
-    int nD = NP, nF = 0, nE = 0;
+    // queue lengths (warp-uniform): DEAD, FLY, TENTATIVE (+ escapes), COLLISION, SURFACE.  Queues are LIFO stacks of slot numbers.
+    int nD = NP, nF = 0, nE = 0, nC = 0, nS = 0;
 
 #define RNG4(out)                                                                                              \
     {                                                                                                          \
@@ -648,8 +664,12 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
         // =========================================================== pick the fullest queue
         __syncwarp();
         const int nDe = exhausted ? 0 : nD;
-        if (nF == 0 && nE == 0 && nDe == 0) break;
-        const int phase = (nE >= nF && nE >= nDe) ? 2 : (nF >= nDe ? 1 : 0);
+        int phase = 0, nbest = nDe;
+        if (nF >= nbest) { phase = 1; nbest = nF; }
+        if (nE >= nbest) { phase = 2; nbest = nE; }
+        if (nC >= nbest) { phase = 3; nbest = nC; }
+        if (nS > nbest) { phase = 4; nbest = nS; }
+        if (nbest == 0) break;
 
         Photon p;
         if (phase == 0) {
@@ -831,86 +851,135 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                 pool_store_flight<NP, PL>(pool, slot, p);
             }
             QPUSH(qF, nF, have && ev == EV_NONE, slot);
-            QPUSH(qE, nE, have && ev != EV_NONE, slot | (ev << 8));
+            QPUSH(qE, nE, have && (ev == EV_TENT || ev == EV_ESC), slot | (ev << 8));
+            QPUSH(qS, nS, have && ev == EV_SFC, slot);
             continue;
         }
 
-        // =========================================================== event phase
-        const int n = min(nE, 32);
-        const bool have = lane < n;
-        int ev = EV_NONE;
-        int slot = 0;
-        if (have) {
-            const int e = int(qE[nE - 1 - lane]);
-            slot = e & 255; ev = e >> 8;
-        }
-        nE -= n;
-        if (have) pool_load<NP>(pool, slot, p, S.Sx, S.Sy);
-        bool alive = have;
-        bool rejected = false;
-        // ---- tentative collisions: accept or reject
-        float4 ev_u = make_float4(0.f, 0.f, 0.f, 0.f);
-        float ev_s3 = 0.0f, ev_uc = 0.0f;
-        int ev_fx = 0, ev_fy = 0, ev_vox = 0;
-        bool ev_in3 = false;
-        if (ev == EV_TENT) {
-            const bool frozen = FZ && (p.flags & FL_FROZEN);
-            const bool ev_empty = (p.flags & FL_EMPTY) != 0;
-            ev_in3 = (p.flags & FL_IN3) != 0;
-            float4 u;
-            RNG4(u);
-            {
-                // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
-                const int4 sb = sm.slabB[p.is];
-                int l0 = sb.x, l1 = sb.y;
-                if (ev_empty) { const int4 gb = sm.grpB[sb.z]; l0 = gb.z; l1 = gb.w; }
-                p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, p.z) : l0;
+        if (phase == 2) {
+            // ======================================================= tentative collisions (and escapes)
+            const int n = min(nE, 32);
+            const bool have = lane < n;
+            int ev = EV_NONE, slot = 0;
+            if (have) {
+                const int e = int(qE[nE - 1 - lane]);
+                slot = e & 255; ev = e >> 8;
             }
-            const int izn = p.iz;
-            float sig = sm.e1tot[izn];
-            float s3 = 0.0f;
-            int fx = 0, fy = 0, vox = 0;
-            if (ev_in3) {
-                if (frozen) { fx = p.cix; fy = p.ciy; }
+            nE -= n;
+            if (have) pool_load<NP>(pool, slot, p, S.Sx, S.Sy);
+            bool accepted = false, rejected = false;
+            float c_apf = 0.0f, c_uz = 0.0f, c_uw = 0.0f, c_s3 = 0.0f;
+            if (ev == EV_ESC) {
+                if (!PL && (p.flags & FL_ABS)) {
+                    const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
+                    const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, S.nz - 1, p.leg, inv_absdz));
+                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    p.w = wn;
+                }
+                ACC(ACC_TOA) += double(p.w);
+            } else if (ev == EV_TENT) {
+                const bool frozen = FZ && (p.flags & FL_FROZEN);
+                const bool ev_empty = (p.flags & FL_EMPTY) != 0;
+                const bool ev_in3 = (p.flags & FL_IN3) != 0;
+                float4 u;
+                RNG4(u);
+                {
+                    // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
+                    const int4 sb = sm.slabB[p.is];
+                    int l0 = sb.x, l1 = sb.y;
+                    if (ev_empty) { const int4 gb = sm.grpB[sb.z]; l0 = gb.z; l1 = gb.w; }
+                    p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, p.z) : l0;
+                }
+                const int izn = p.iz;
+                float sig = sm.e1tot[izn];
+                float s3 = 0.0f;
+                int fx = 0, fy = 0, vox = 0;
+                if (ev_in3) {
+                    if (frozen) { fx = p.cix; fy = p.ciy; }
+                    else {
+                        const int shx = ev_empty ? S.shx : 0, shy = ev_empty ? S.shy : 0;
+                        const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
+                        const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
+                        fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
+                        fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
+                    }
+                    vox = ((izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                    if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT(CNT_TENT)++; }
+                }
+                p.tau = -__logf(u.y);
+                float uc = u.x * p.M;
+                if (!(uc < sig)) rejected = true;
                 else {
-                    const int shx = ev_empty ? S.shx : 0, shy = ev_empty ? S.shy : 0;
-                    const int ixlo = (p.cix >> shx) << shx, ixhi = ixlo + (1 << shx);
-                    const int iylo = (p.ciy >> shy) << shy, iyhi = iylo + (1 << shy);
-                    fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
-                    fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
+                    // ---- real collision: gas absorption of the finished leg, scattering component, implicit capture
+                    if (!PL && (p.flags & FL_ABS)) {
+                        const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
+                        const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, izn, p.leg, inv_absdz));
+                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        p.w = wn;
+                    }
+                    float omg = 1.0f, apf = 0.0f;
+                    bool found = false;
+                    if (uc < s3) {
+                        if (S.np3d == 1) {
+                            const float2 pr = __ldg(S.prop3 + vox);
+                            omg = pr.x; apf = pr.y; found = true;
+                        } else {
+                            const size_t n3 = size_t(S.nz3) * nxy;
+                            for (int k = 0; k < S.np3d; ++k) {
+                                const float e = __ldg(S.ext3 + size_t(k) * n3 + vox);
+                                if (uc < e || k == S.np3d - 1) {
+                                    const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + vox);
+                                    omg = pr.x; apf = pr.y; found = true;
+                                    break;
+                                }
+                                uc -= e;
+                            }
+                        }
+                    } else uc -= s3;
+                    if (!found) {
+                        for (int k = 0; k < S.np1d; ++k) {
+                            const float e = sm.e1[k * S.nz + izn];
+                            if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
+                            uc -= e;
+                        }
+                    }
+                    CNT(CNT_COLL)++;
+                    const float wn = p.w * omg;
+                    if (wn < p.w) {
+                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
+                    }
+                    p.w = wn;
+                    p.order++; p.flags &= ~FL_DIRECT;
+                    if (p.w > 0.0f) {
+                        accepted = true;
+                        c_apf = apf; c_uz = u.z; c_uw = u.w; c_s3 = s3;
+                        // the fine cell indices follow the collision point (it may lie anywhere in an empty coarse cell)
+                        if (ev_in3 && !frozen) { p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy); }
+                    }
                 }
-                vox = ((izn - S.iz0) * S.ny + fy) * S.nx + fx;
-                if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT(CNT_TENT)++; }
             }
-            p.tau = -__logf(u.y);
-            const float uc = u.x * p.M;
-            if (uc < sig) {
-                ev = EV_COLL;
-                ev_u = u; ev_uc = uc; ev_s3 = s3; ev_fx = fx; ev_fy = fy; ev_vox = vox;
-                if (ev_in3 && ev_empty && !frozen) {
-                    // keep the fine cell indices consistent with the position inside the coarse cell
-                    p.cix = min(S.ncx - 1, fx / S.svx); p.ciy = min(S.ncy - 1, fy / S.svy);
-                }
-            } else { ev = EV_NONE; rejected = true; }
+            if (rejected) pool_store_reject<NP>(pool, slot, p);
+            if (accepted) pool_store_accept<NP>(pool, slot, p, c_apf, c_uz, c_uw, c_s3);
+            QPUSH(qF, nF, rejected, slot);
+            QPUSH(qC, nC, accepted, slot);
+            QPUSH(qD, nD, have && !rejected && !accepted, slot);
+            continue;
         }
 
-        // ---- events (real collisions, surface hits, escapes)
-        if (ev != EV_NONE) do {
-            const int evk = ev;
-            const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
-            // path-integrated gas absorption of the leg that ends here
-            const int izb = (evk == EV_SFC) ? 0 : (evk == EV_ESC ? S.nz - 1 : p.iz);
-            if (evk == EV_SFC) { p.iz = 0; p.is = 0; p.z = sm.z[0]; p.flags &= ~FL_STALE; }
-            if (!PL && (p.flags & FL_ABS)) {
-                const float ta = abs_tau(S, sm, p.job, p.za, p.iza, p.z, izb, p.leg, inv_absdz);
-                const float wn = p.w * __expf(-ta);
-                ACC(ACC_ATM) += double(p.w) - double(wn);
-                p.w = wn;
-            }
-            p.za = p.z; p.iza = izb; p.leg = 0.0f;
-            if (evk == EV_ESC) { ACC(ACC_TOA) += double(p.w); alive = false; break; }
-
-            float4 u;
+        // =========================================================== event phase: collisions (phase 3) or surface hits (4)
+        // The two kinds come from separate queues, so a warp works on one kind at a time; they share the local estimate,
+        // the roulette and the write-back.
+        const int evk = phase == 3 ? EV_COLL : EV_SFC;
+        int n, slot = 0;
+        if (phase == 3) { n = min(nC, 32); if (lane < n) slot = int(qC[nC - 1 - lane]); nC -= n; }
+        else { n = min(nS, 32); if (lane < n) slot = int(qS[nS - 1 - lane]); nS -= n; }
+        const bool have = lane < n;
+        float c_uw = 0.0f;
+        if (have) { pool_load<NP>(pool, slot, p, S.Sx, S.Sy); c_uw = pool[F_AUX * NP + slot]; }
+        bool alive = have;
+        if (have) do {
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
             float3 newd;
             float apf = 0.0f;
             int fx = 0, fy = 0;
@@ -919,47 +988,16 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
             float prm[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             const float3 wi = make_float3(-p.d.x, -p.d.y, -p.d.z);
             if (evk == EV_COLL) {
-                // ---- real collision: pick the scattering component (uc is uniform on [0, sig))
-                u = ev_u;
-                fx = ev_fx; fy = ev_fy; s3 = ev_s3;
-                float uc = ev_uc;
-                const int izn = p.iz;
-                float omg = 1.0f;
-                bool found = false;
-                if (uc < s3) {
-                    if (S.np3d == 1) {
-                        const float2 pr = __ldg(S.prop3 + ev_vox);
-                        omg = pr.x; apf = pr.y; found = true;
-                    } else {
-                        const size_t n3 = size_t(S.nz3) * nxy;
-                        for (int k = 0; k < S.np3d; ++k) {
-                            const float e = __ldg(S.ext3 + size_t(k) * n3 + ev_vox);
-                            if (uc < e || k == S.np3d - 1) {
-                                const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + ev_vox);
-                                omg = pr.x; apf = pr.y; found = true;
-                                break;
-                            }
-                            uc -= e;
-                        }
-                    }
-                } else uc -= s3;
-                if (!found) {
-                    for (int k = 0; k < S.np1d; ++k) {
-                        const float e = sm.e1[k * S.nz + izn];
-                        if (uc < e || k == S.np1d - 1) { omg = sm.o1[k * S.nz + izn]; apf = sm.a1[k * S.nz + izn]; break; }
-                        uc -= e;
+                // ---- hand-over record of the tentative phase (pool_store_accept)
+                apf = p.leg; u.z = p.za; u.w = c_uw; s3 = p.M;
+                const bool ev_in3 = (p.flags & FL_IN3) != 0;
+                if (ev_in3) {
+                    if (FZ && (p.flags & FL_FROZEN)) { fx = p.cix; fy = p.ciy; }
+                    else {
+                        fx = min(min(S.nx, (p.cix + 1) * S.svx) - 1, max(p.cix * S.svx, int(p.x * S.inv_dx)));
+                        fy = min(min(S.ny, (p.ciy + 1) * S.svy) - 1, max(p.ciy * S.svy, int(p.y * S.inv_dy)));
                     }
                 }
-                CNT(CNT_COLL)++;
-                // implicit capture
-                const float wn = p.w * omg;
-                if (wn < p.w) {
-                    ACC(ACC_ATM) += double(p.w) - double(wn);
-                    if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
-                }
-                p.w = wn;
-                p.order++; p.flags &= ~FL_DIRECT;
-                if (!(p.w > 0.0f)) { alive = false; break; }
                 if (FZ && S.solver == B200RT_SOLVER_PARTIAL_3D && p.order >= S.iso_ss && !(p.flags & FL_FROZEN)) {
                     if (!ev_in3) { p.cix = min(S.nx - 1, int(p.x * S.inv_dx)); p.ciy = min(S.ny - 1, int(p.y * S.inv_dy)); }
                     else { p.cix = fx; p.ciy = fy; }
@@ -967,7 +1005,14 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     p.flags |= FL_FROZEN;
                 }
             } else {
-                // ---- surface hit
+                // ---- surface hit: path-integrated gas absorption of the leg that ends here
+                p.iz = 0; p.is = 0; p.z = sm.z[0]; p.flags &= ~FL_STALE;
+                if (!PL && (p.flags & FL_ABS)) {
+                    const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
+                    const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, 0, p.leg, inv_absdz));
+                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    p.w = wn;
+                }
                 CNT(CNT_SFC)++;
                 RNG4(u);
                 const bool frozen = FZ && (p.flags & FL_FROZEN);
@@ -989,6 +1034,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
                     s3 = __ldg(S.ext3tot + fy * S.nx + fx);
                 }
             }
+            p.za = p.z; p.iza = p.iz; p.leg = 0.0f;
 
             // ---- local estimates toward every sensor (shared by both event kinds)
             if (want_rad) {
@@ -1048,9 +1094,7 @@ __global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_co
             if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
         } while (0);
 
-        if (have && alive) {
-            if (rejected) pool_store_reject<NP>(pool, slot, p); else pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
-        }
+        if (have && alive) pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
         QPUSH(qF, nF, have && alive, slot);
         QPUSH(qD, nD, have && !alive, slot);
     }
