@@ -21,8 +21,16 @@
 #include <vector>
 
 #define MAX_SENS 16
+// Launch shape of the transport kernel.  Warps are independent (per-warp photon pools, no block-level synchronisation
+// after the table staging), so the block size only sets the granularity.  A B200 SM sub-partition holds 16 K registers:
+// 5 warps per scheduler need <= 96 registers per thread (tools/sweep_pool.py: 20 warps/SM at 96 registers beat 16 warps
+// at 123 registers by 4.5 % although ptxas then spills 48 bytes per thread).  Two blocks of 10 warps keep the per-block
+// tables (and the 1 KB the driver reserves per block) from eating the shared memory the photon pools need.
+#ifndef RT_TPB
+#define RT_TPB 320
+#endif
 #ifndef RT_MINB
-#define RT_MINB 2   // resident 256-thread blocks per SM the register allocation aims at
+#define RT_MINB 2
 #endif
 
 // ============================================================================ device structs
@@ -580,7 +588,7 @@ __device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, f
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
 template <bool PL, bool FZ, int NP>
-__global__ void __launch_bounds__(256, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
+__global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
     Smem sm;
     float* pool;
@@ -1352,7 +1360,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
 
     // ------------------------------------------------ super-voxel grid
     const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0;
-    // auto sizes: fine cells of 2 x 2 columns and as many layers as make them roughly cubic; coarse (empty-space)
+    // auto sizes: fine cells of 2 x 2 columns and as many layers as make them 0.6 x as high as wide; coarse (empty-space)
     // cells of 4 x 4 fine cells horizontally and about the same physical height (tuned on the config-2 scene,
     // tools/sweep_sv.py; any choice is unbiased, tests/test_gpu_parity.py sweeps several)
     int svx = opt->svx > 0 ? opt->svx : 2, svy = opt->svy > 0 ? opt->svy : 2, svz = opt->svz;
@@ -1360,7 +1368,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         svz = 1;
         if (nz3 > 1) {
             const double dz_mean = (zg[iz0 + nz3] - zg[iz0]) / nz3;
-            svz = int(std::lround(svx * sc->dx / dz_mean));
+            svz = std::max(1, int(std::lround(0.6 * svx * sc->dx / dz_mean)));
         }
     }
     if (opt->solver != B200RT_SOLVER_3D) { svx = 1; svy = 1; }     // column-frozen modes need cell == column
@@ -1672,8 +1680,8 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     CK(cudaMemsetAsync(H->stats.p, 0, sizeof(DevStats), st));
 
     // launch shape: the per-warp photon pools decide how many blocks fit on an SM (shared memory), see DESIGN.md
-    int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : 256;
-    tpb = std::min(256, std::max(32, (tpb / 32) * 32));
+    int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : RT_TPB;
+    tpb = std::min(RT_TPB, std::max(32, (tpb / 32) * 32));
     const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, np);

@@ -14,8 +14,8 @@ MARKS = [('pool_load/store', 'void pool_load'), ('wrapf', 'float wrapf'), ('tall
          ('le_tau', 'float le_tau('), ('le_deposit', 'void le_deposit'), ('inv_dir', 'float3 inv_dir'),
          ('surface_sample', 'float surface_sample'), ('kernel setup', 'transport_kernel(const __grid_constant__'),
          ('queue pick', 'pick the fullest queue'), ('regeneration', '= regeneration'), ('flight', '= flight: geometry only'),
-         ('event: load+tag', '= event phase'), ('event: tentative', '---- tentative collisions: accept or reject'),
-         ('event: collision/surface', '---- events (real collisions'), ('event: local estimate', '---- local estimates toward every sensor'),
+         ('tentative phase', '= tentative collisions (and escapes)'), ('event: load', '= event phase: collisions'),
+         ('event: collision/surface', '---- hand-over record of the tentative phase'), ('event: local estimate', '---- local estimates toward every sensor'),
          ('event: new direction+roulette', '---- new direction'), ('flush', '---- flush the per-thread event counters'),
          ('(end)', 'typedef void (*transport_fn)')]
 starts = []
