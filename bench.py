@@ -16,7 +16,6 @@ Rank 0 prints ONE JSON line.
 """
 
 import argparse
-import datetime
 import json
 import os
 import subprocess
@@ -33,23 +32,10 @@ SEED = 20260101
 
 
 def build_workload(nx=480, ny=480, nz3=100, photons=1e8, nrun=3):
-    """BASELINE.json configs[1] as synthetic input (SURVEY.md 8d 'C2'): returns kwargs for mcarats_ng + abs object."""
-    from er3t_b200.pre import atm_atmmod, abs_16g, pha_mie_wc, cld_gen_les
-    from er3t_b200.rtm.mca import mca_atm_1d, mca_atm_3d, mca_sca
-    dz = 4.0 / nz3                                               # 3-D block spans 0.5 .. 4.5 km
-    levels = np.concatenate(([0.0], 0.5 + dz * np.arange(nz3 + 1), np.arange(5.0, 20.1, 1.0)))
-    atm0 = atm_atmmod(levels=levels)
-    abs0 = abs_16g(wavelength=650.0, atm_obj=atm0)
-    cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=0.1, dy=0.1, altitude=0.5 + dz * (np.arange(nz3) + 0.5), seed=2, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=650.0)
-    sca = mca_sca(pha_obj=pha0)
-    atm3d0 = mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True)
-    atm1d0 = mca_atm_1d(atm_obj=atm0, abs_obj=abs0)
-    kw = dict(date=datetime.datetime(2017, 8, 13), atm_1ds=[atm1d0], atm_3ds=[atm3d0], Ng=abs0.Ng, target='radiance',
-              surface_albedo=0.03, sca=sca, solar_zenith_angle=28.9, solar_azimuth_angle=296.83,
-              sensor_zenith_angle=0.0, sensor_azimuth_angle=0.0, sensor_altitude=705000.0, fdir='tmp-data/bench',
-              Nrun=nrun, photons=photons, weights=abs0.coef['weight']['data'], solver='3D', quiet=True, seed=SEED,
-              iz3l_fix=True)
+    """BASELINE.json configs[1] as synthetic input (SURVEY.md 8d 'C2', workloads.c2): kwargs for mcarats_ng + abs object."""
+    import workloads
+    kw, abs0 = workloads.c2(scale=1.0, photons=photons, nx=nx, ny=ny, nz3=nz3, nrun=nrun)
+    kw['fdir'] = 'tmp-data/bench'
     return kw, abs0
 
 

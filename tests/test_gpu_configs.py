@@ -1,0 +1,147 @@
+"""
+The five BASELINE.json configs (workloads.py) through the PUBLIC API -- mcarats_ng + mca_out_ng -- on
+the GPU against the same call driven through the oracle-backed test double, at sizes the oracle finishes in seconds;
+then the named full-size C2 shape through size-independent properties (energy closure, photon count, finiteness).
+
+Criteria (north_star): R + T + A = 1 to fp64-accumulation precision; domain-mean fluxes / radiances within 0.5 % (or,
+when the Monte Carlo noise of the comparison itself exceeds that, within 3.5 combined standard errors); per-pixel
+radiance within 3 combined sigma.
+"""
+
+import numpy as np
+import pytest
+
+import workloads
+from er3t_b200.rtm import mca as bmca
+from oracle_solver import OracleSolver
+
+pytestmark = pytest.mark.gpu
+
+NRUN = 10          # runs per side: the per-pixel z-scores follow a Student-t with few degrees of freedom (heavy tails)
+
+
+def _balance(st):
+    return (st['w_toa_up'] + st['w_sfc_abs'] + st['w_atm_abs'] - st['w_roulette']) / st['photons'] - 1.0
+
+
+def _both(kw, abs0, solver, photons_gpu, photons_cpu, tmp_path):
+    kw = dict(kw, Nrun=NRUN, fdir=str(tmp_path))
+    mg = bmca.mcarats_ng(**dict(kw, photons=photons_gpu, seed=7, solver_obj=solver))
+    mc = bmca.mcarats_ng(**dict(kw, photons=photons_cpu, seed=1007, solver_obj=OracleSolver()))
+    assert abs(_balance(mg.stats)) < 1e-9 and abs(_balance(mc.stats)) < 1e-9
+    g = bmca.mca_out_ng(mca_obj=mg, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data
+    c = bmca.mca_out_ng(mca_obj=mc, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data
+    return mg, g, c
+
+
+def _mean_ok(g, c, axes):
+    """domain means per run -> within 0.5 % or 3.5 combined standard errors"""
+    gr, cr = g.mean(axis=axes), c.mean(axis=axes)                  # (Nrun,)
+    gm, cm = gr.mean(), cr.mean()
+    se = np.hypot(gr.std(ddof=1), cr.std(ddof=1)) / np.sqrt(NRUN)
+    return abs(gm / cm - 1.0) < 0.005 or abs(gm - cm) < 3.5 * se, (gm, cm, se)
+
+
+def _pixels_ok(g, c):
+    gm, gs = g.mean(axis=-1), g.std(axis=-1, ddof=1) / np.sqrt(NRUN)
+    cm, cs = c.mean(axis=-1), c.std(axis=-1, ddof=1) / np.sqrt(NRUN)
+    den = np.sqrt(gs ** 2 + cs ** 2) + 2e-6 * np.abs(cm)
+    z = (gm - cm)[den > 0] / den[den > 0]
+    # t(9): P(|z| > 3) = 1.5 %, P(|z| > 9) = 1e-5 per pixel
+    return np.mean(np.abs(z) > 3.0) <= 0.04 and np.max(np.abs(z)) < 9.0, (float(np.mean(np.abs(z) > 3.0)), float(np.max(np.abs(z))))
+
+
+@pytest.mark.parametrize('hom3d', [False, True])
+def test_c1_plane_parallel_flux(solver, tmp_path, hom3d):
+    kw, abs0 = workloads.build('C1', hom3d=hom3d)
+    mg, g, c = _both(kw, abs0, solver, 1e6, 2e5, tmp_path)
+    for key in ('f_up', 'f_down', 'f_down_direct'):
+        a, b = np.asarray(g[key]['data']), np.asarray(c[key]['data'])          # (Nx, Ny, Nz+1, Nrun)
+        for lev in (0, -1):
+            ok, info = _mean_ok(a[:, :, lev, :], b[:, :, lev, :], (0, 1))
+            if b[:, :, lev, :].mean() > 1e-3:
+                assert ok, (key, lev, info)
+    # direct beam at the surface: mu0 * exp(-tau / mu0) weighted over g is what both sides must reproduce; TOA down-flux is exact
+    assert np.allclose(np.asarray(g['f_down']['data'])[:, :, -1, :].mean(), np.asarray(c['f_down']['data'])[:, :, -1, :].mean(), rtol=1e-5)
+
+
+def test_c2_les_radiance(solver, tmp_path):
+    kw, abs0 = workloads.build('C2', scale=0.004)
+    mg, g, c = _both(kw, abs0, solver, 3e6, 3e5, tmp_path)
+    a, b = np.asarray(g['rad']['data']), np.asarray(c['rad']['data'])
+    ok, info = _mean_ok(a, b, (0, 1)); assert ok, info
+    ok, info = _pixels_ok(a, b); assert ok, info
+
+
+def test_c3_lsrt_multi_angle(solver, tmp_path):
+    kw, abs0 = workloads.build('C3', scale=0.004)
+    kw = dict(kw, Nrun=NRUN, fdir=str(tmp_path))
+    mg = bmca.mcarats_ng(**dict(kw, photons=3e6, seed=7, solver_obj=solver))
+    mc = bmca.mcarats_ng(**dict(kw, photons=3e5, seed=1007, solver_obj=OracleSolver()))
+    assert abs(_balance(mg.stats)) < 1e-9
+    g = bmca.mca_out_ng(mca_obj=mg, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data['rad']['data']
+    c = bmca.mca_out_ng(mca_obj=mc, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data['rad']['data']
+    ok, info = _mean_ok(np.asarray(g), np.asarray(c), (0, 1)); assert ok, info
+    ok, info = _pixels_ok(np.asarray(g), np.asarray(c)); assert ok, info
+    # the oblique views ride along as extra sensors: (nx, ny, Nrun) each, already g-weighted
+    assert len(mg.rad_extra) == 2 and len(mc.rad_extra) == 2
+    for k in range(2):
+        ok, info = _mean_ok(mg.rad_extra[k], mc.rad_extra[k], (0, 1)); assert ok, (k, info)
+        ok, info = _pixels_ok(mg.rad_extra[k], mc.rad_extra[k]); assert ok, (k, info)
+
+
+def test_c4_o2a_band_g_sweep(solver, tmp_path):
+    """Absorption grows from the line wing to the line centre: radiance must fall monotonically, and each wavelength
+    must match the oracle."""
+    means = []
+    for iw, (kw, abs0) in enumerate(workloads.build('C4', scale=0.001, nwvl=3)):
+        mg, g, c = _both(kw, abs0, solver, 2e6, 2e5, tmp_path / ('w%d' % iw))
+        a, b = np.asarray(g['rad']['data']), np.asarray(c['rad']['data'])
+        ok, info = _mean_ok(a, b, (0, 1)); assert ok, (iw, info)
+        ok, info = _pixels_ok(a, b); assert ok, (iw, info)
+        means.append(a.mean() / float(g['toa']['data']))
+    assert means[0] > means[1] > means[2]
+
+
+def test_c5_flux_over_cox_munk_ocean(solver, tmp_path):
+    kw, abs0 = workloads.build('C5', scale=0.06)
+    mg, g, c = _both(kw, abs0, solver, 2e6, 2e5, tmp_path)
+    for key in ('f_up', 'f_down'):
+        a, b = np.asarray(g[key]['data']), np.asarray(c[key]['data'])
+        for lev in (0, 3, -1):
+            ok, info = _mean_ok(a[:, :, lev, :], b[:, :, lev, :], (0, 1)); assert ok, (key, lev, info)
+    # per-column surface down-flux field
+    ok, info = _pixels_ok(np.asarray(g['f_down']['data'])[:, :, 0, :], np.asarray(c['f_down']['data'])[:, :, 0, :]); assert ok, info
+
+
+def test_c2_named_shape_properties(solver, tmp_path):
+    """480 x 480 x 100 voxels (BASELINE.json configs[1]) at a photon count the test budget allows: every photon traced
+    exactly once, energy closes to fp64 rounding, radiance finite and positive, cloudy pixels brighter than clear ones."""
+    kw, abs0 = workloads.build('C2')
+    m = bmca.mcarats_ng(**dict(kw, photons=2e7, Nrun=3, solver_obj=solver, fdir=str(tmp_path)))
+    st = m.stats
+    assert st['photons'] == int(np.sum(m.photons))
+    assert abs(_balance(st)) < 1e-9
+    out = bmca.mca_out_ng(mca_obj=m, abs_obj=abs0, mode='mean', squeeze=True, quiet=True).data
+    rad = np.asarray(out['rad']['data'])
+    assert rad.shape == (480, 480) and np.all(np.isfinite(rad)) and rad.min() >= 0.0
+    cot = m.atm_3ds[0].cld.lev['cot_2d']['data']
+    assert rad[cot > 5.0].mean() > 3.0 * rad[cot == 0.0].mean()
+
+
+def test_batched_lut_driver_on_gpu(solver):
+    """func_ref_vs_cot: all COT values in one IPA launch on the GPU against the same table from the oracle double."""
+    import datetime
+    import er3t_b200.pre as bpre
+    atm0 = bpre.atm_atmmod(levels=np.linspace(0, 20, 21))
+    abs0 = bpre.abs_16g(wavelength=650.0, atm_obj=atm0)
+    pha0 = bpre.pha_mie_wc(wavelength=650.0, reff=[5.0, 10.0, 15.0], nr=48)
+    cot = np.array([0.0, 1.0, 4.0, 16.0, 64.0])
+    kw = dict(cer0=10.0, fdir=None, date=datetime.datetime(2017, 8, 13), wavelength=650.0, surface_albedo=0.03, solar_zenith_angle=30.0,
+              atm0=atm0, pha0=pha0, abs0=abs0, Nrun=NRUN)
+    fg = bmca.func_ref_vs_cot(cot, Nphoton=4e5, seed=5, solver_obj=solver, **kw)
+    fc = bmca.func_ref_vs_cot(cot, Nphoton=4e4, seed=1005, solver_obj=OracleSolver(), **kw)
+    assert np.all(np.diff(fg.ref) > 0)
+    se = np.hypot(fg.ref_std, fc.ref_std) / np.sqrt(NRUN)
+    assert np.all(np.abs(fg.ref - fc.ref) < 4.0 * se + 0.002), (fg.ref, fc.ref, se)
+    assert abs(float(fg.get_cot_from_ref(fg.ref[3], method='linear')) - 16.0) < 1e-6
