@@ -273,6 +273,9 @@ def main():
            'steps': esteps, 'ms_per_step': 1e3 * dt / esteps,
            'api': 'er3t_b200.rtm.mca.mcarats_ng(...) + mca_out_ng(...) with host numpy inputs (pageable memory)'}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()

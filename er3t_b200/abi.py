@@ -29,7 +29,9 @@ _ip = C.POINTER(C.c_int32)
 
 class Sensor(C.Structure):
     _fields_ = [('kind', C.c_int32), ('nxr', C.c_int32), ('nyr', C.c_int32), ('_pad', C.c_int32),
-                ('the', C.c_double), ('phi', C.c_double), ('zloc', C.c_double), ('zref', C.c_double)]
+                ('the', C.c_double), ('phi', C.c_double), ('zloc', C.c_double), ('zref', C.c_double),
+                ('psi', C.c_double), ('xpos', C.c_double), ('ypos', C.c_double), ('qmax', C.c_double),
+                ('umax', C.c_double), ('vmax', C.c_double), ('apsize', C.c_double)]
 
 
 class SceneStruct(C.Structure):
@@ -244,6 +246,9 @@ class HostScene:
             se.nxr, se.nyr = int(q.get('nxr', nx)), int(q.get('nyr', ny))
             se.the, se.phi = float(q.get('the', 180.0)), float(q.get('phi', 270.0))
             se.zloc, se.zref = float(q.get('zloc', 705000.0)), float(q.get('zref', 0.0))
+            se.psi, se.xpos, se.ypos = float(q.get('psi', 0.0)), float(q.get('xpos', 0.5)), float(q.get('ypos', 0.5))
+            se.qmax, se.umax, se.vmax = float(q.get('qmax', 180.0)), float(q.get('umax', 180.0)), float(q.get('vmax', 180.0))
+            se.apsize = float(q.get('apsize', 0.0))
         s.nrad = len(sensors)
         s.sensors = C.cast(self.sensors, C.POINTER(Sensor))
         self.struct = s

@@ -45,7 +45,14 @@ struct DevSensor {
     int vertical_up;     // s == (0,0,1): precomputed tau-to-top table applies in 3-D mode
     int fast_ok;         // zt is at/above the top of the 3-D block
     long long off;       // offset of this sensor inside a radiance slab
-    double npix;         // nxr * nyr
+    double npix;         // kind 2: nxr * nyr ; kind 1: domain area Lx * Ly (m^2)
+    // all-sky camera (kind 1): `s` is the viewing axis, (ex, ey) complete the camera frame
+    int kind;
+    float3 cpos, ex, ey;
+    float cos_half_fov;  // cos(qmax / 2)
+    float u_half, v_half;        // umax / 2, vmax / 2 (rad)
+    float pix_per_u, pix_per_v;  // nxr / umax, nyr / vmax (pixels per rad)
+    float ap2;           // apsize^2
 };
 
 struct DevJob {
@@ -413,8 +420,9 @@ __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int 
 // exact traversal toward a sensor: layer by layer, column by column inside the 3-D block (oblique views, sensors
 // inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.  Everything is passed by value so
 // that the photon never has to live in local memory.
+struct RayTarget { float3 s; float zt; };   // unit direction of travel and the level at which the integral stops
 __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __restrict__ smz, const float* __restrict__ sme1tot,
-                                             const DevSensor& se, float x, float y, float z, int iz, int job, int has_abs,
+                                             const RayTarget se, float x, float y, float z, int iz, int job, int has_abs,
                                              int frozen, int fx, int fy, bool in3, unsigned* n_visit_out) {
     const float* ab = S.job_abs + size_t(job) * S.nz;
     const int nxy = S.nx * S.ny;
@@ -506,7 +514,8 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
     }
     if (frozen) { fx = p.cix; fy = p.ciy; }
     unsigned nv = 0;
-    const float t = le_tau_generic(S, sm.z, sm.e1tot, se, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
+    const RayTarget rt = {se.s, se.zt};
+    const float t = le_tau_generic(S, sm.z, sm.e1tot, rt, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
     CNT(CNT_VISIT) += nv;
     return t;
 }
@@ -530,6 +539,48 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
     tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
     CNT(CNT_LE)++;
     CNT(CNT_TALLY)++;
+}
+
+// All-sky camera (Rad_mrkind = 1): contribution of one event, per unit photon weight, to the radiance the camera at
+// se.cpos records in the pixel that sees the event.  Returns 0 when the event lies outside the field of view.
+//   I_pix += w * f(event -> camera) * exp(-tau) / (R^2 * dOmega_pix)          [times the power one photon carries]
+// Periodic domain: the nearest image of the camera is used.  Polar pixel mapping: U = theta cos(az), V = theta sin(az);
+// a pixel of size dU x dV subtends dOmega = (sin(theta) / theta) dU dV.
+__device__ __noinline__ float camera_le(const DevScene& S, const float* __restrict__ smz, const float* __restrict__ sme1tot,
+                                        const DevSensor& se, float x, float y, float z, int iz, int job, int has_abs, int fx, int fy,
+                                        bool in3, const float3 din, int evk, float apf, int sfc_type, float p0, float p1, float p2,
+                                        float p3, float p4, int* pix_out, unsigned* n_visit_out) {
+    *n_visit_out = 0;
+    float dx = se.cpos.x - x, dy = se.cpos.y - y;
+    dx -= S.Lx * rintf(dx * S.inv_Lx);
+    dy -= S.Ly * rintf(dy * S.inv_Ly);
+    const float dz = se.cpos.z - z;
+    const float R2 = dx * dx + dy * dy + dz * dz;
+    if (!(R2 > 1e-6f) || fabsf(dz) < 1e-3f) return 0.0f;
+    const float invR = rsqrtf(R2);
+    const float3 sdir = make_float3(dx * invR, dy * invR, dz * invR);          // event -> camera
+    if (fabsf(sdir.z) < 1e-4f) return 0.0f;
+    // direction in which the camera sees the event
+    const float3 v = make_float3(-sdir.x, -sdir.y, -sdir.z);
+    const float cq = v.x * se.s.x + v.y * se.s.y + v.z * se.s.z;
+    if (cq < se.cos_half_fov) return 0.0f;
+    const float theta = acosf(fminf(1.0f, cq));
+    const float vx = v.x * se.ex.x + v.y * se.ex.y + v.z * se.ex.z, vy = v.x * se.ey.x + v.y * se.ey.y + v.z * se.ey.z;
+    const float rho = sqrtf(vx * vx + vy * vy);
+    const float U = rho > 0.0f ? theta * vx / rho : 0.0f, V = rho > 0.0f ? theta * vy / rho : 0.0f;
+    if (fabsf(U) >= se.u_half || fabsf(V) >= se.v_half) return 0.0f;
+    const int px = min(se.nxr - 1, max(0, int((U + se.u_half) * se.pix_per_u)));
+    const int py = min(se.nyr - 1, max(0, int((V + se.v_half) * se.pix_per_v)));
+    *pix_out = py * se.nxr + px;
+    float f;
+    if (evk == EV_COLL) f = phase_eval(S.pt, apf, din.x * sdir.x + din.y * sdir.y + din.z * sdir.z) * (0.25f / RT_PI);
+    else f = sdir.z > 0.0f ? brdf_eval(sfc_type, p0, p1, p2, p3, p4, make_float3(-din.x, -din.y, -din.z), sdir) * sdir.z : 0.0f;
+    if (!(f > 0.0f)) return 0.0f;
+    const RayTarget rt = {sdir, se.cpos.z};
+    const float tau = le_tau_generic(S, smz, sme1tot, rt, x, y, z, iz, job, has_abs, 0, fx, fy, in3, n_visit_out);
+    const float sinc = theta > 1e-4f ? __sinf(theta) / theta : 1.0f;
+    const float domega = sinc / (se.pix_per_u * se.pix_per_v);
+    return f * __expf(-tau) / (fmaxf(R2, se.ap2) * domega);
 }
 
 __device__ __forceinline__ float3 inv_dir(const float3 d) {
@@ -587,7 +638,7 @@ __device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, f
 // only synchronisation is __syncwarp.
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
-template <bool PL, bool FZ, int NP>
+template <bool PL, bool FZ, int NP, bool CAM>
 __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
     Smem sm;
@@ -1048,6 +1099,21 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             if (want_rad) {
                 for (int k = 0; k < S.nrad; ++k) {
                     const DevSensor& se = S.sens[k];
+                    if (CAM && se.kind == 1) {
+                        int pix = 0;
+                        unsigned nv = 0;
+                        const bool in3 = (S.nz3 > 0) && p.iz >= S.iz0 && p.iz < S.iz0 + S.nz3;
+                        const float c = camera_le(S, sm.z, sm.e1tot, se, p.x, p.y, p.z, p.iz, p.job, p.flags & FL_ABS, fx, fy, in3, p.d, evk, apf,
+                                                  sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], &pix, &nv);
+                        CNT(CNT_VISIT) += nv;
+                        if (c > 0.0f) {
+                            const DevJob& J = S.jobs[p.job];
+                            tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
+                            CNT(CNT_LE)++;
+                            CNT(CNT_TALLY)++;
+                        }
+                        continue;
+                    }
                     const float dzs = (se.zt - p.z) * se.s.z;
                     if (!(dzs > 0.0f)) continue;
                     float f;
@@ -1138,16 +1204,19 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 
 typedef void (*transport_fn)(const DevScene);
 template <int NP>
-static transport_fn pick_transport_np(bool pl, bool fz) {
-    if (pl) return fz ? transport_kernel<true, true, NP> : transport_kernel<true, false, NP>;
-    return fz ? transport_kernel<false, true, NP> : transport_kernel<false, false, NP>;
+static transport_fn pick_transport_np(bool pl, bool fz, bool cam) {
+    // CAM (all-sky camera sensors present) is its own specialisation: the camera's local estimate is a large cold path
+    // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false)
+    if (cam) return pl ? transport_kernel<true, false, NP, true> : transport_kernel<false, false, NP, true>;
+    if (pl) return fz ? transport_kernel<true, true, NP, false> : transport_kernel<true, false, NP, false>;
+    return fz ? transport_kernel<false, true, NP, false> : transport_kernel<false, false, NP, false>;
 }
-static transport_fn pick_transport(bool pl, bool fz, int np) {
+static transport_fn pick_transport(bool pl, bool fz, bool cam, int np) {
     switch (np) {
-        case 32: return pick_transport_np<32>(pl, fz);
-        case 64: return pick_transport_np<64>(pl, fz);
-        case 128: return pick_transport_np<128>(pl, fz);
-        default: return pick_transport_np<96>(pl, fz);
+        case 32: return pick_transport_np<32>(pl, fz, cam);
+        case 64: return pick_transport_np<64>(pl, fz, cam);
+        case 128: return pick_transport_np<128>(pl, fz, cam);
+        default: return pick_transport_np<96>(pl, fz, cam);
     }
 }
 
@@ -1195,7 +1264,7 @@ struct Handle {
     int numSM = 0;
     size_t smem_bytes = 0, smem_tables = 0;
     int pool_slots = 0;
-    bool k_pl = false, k_fz = false;
+    bool k_pl = false, k_fz = false, k_cam = false;
     // owned device memory
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3;
@@ -1574,10 +1643,31 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     long long off = 0;
     for (int k = 0; k < sc->nrad; ++k) {
         const b200rt_sensor& q = sc->sensors[k];
-        if (q.kind != 2) return fail(H, B200RT_ERR_ARG, "only Rad_mrkind = 2 (satellite) sensors are implemented");
+        if (q.kind != 2 && q.kind != 1) return fail(H, B200RT_ERR_ARG, "Rad_mrkind must be 1 (all-sky camera) or 2 (satellite)");
         if (q.nxr < 1 || q.nyr < 1) return fail(H, B200RT_ERR_ARG, "sensor pixel grid must be >= 1 x 1");
         const float3 view = dir_from_angles(q.the, q.phi);
         DevSensor& se = S.sens[k];
+        se.kind = q.kind;
+        if (q.kind == 1) {
+            if (opt->solver != B200RT_SOLVER_3D) return fail(H, B200RT_ERR_ARG, "the all-sky camera needs the 3-D solver");
+            if (!(q.qmax > 0 && q.qmax <= 360) || !(q.umax > 0) || !(q.vmax > 0)) return fail(H, B200RT_ERR_ARG, "camera: qmax, umax, vmax must be > 0");
+            const double t = q.the * M_PI / 180.0, f = q.phi * M_PI / 180.0, ps = q.psi * M_PI / 180.0;
+            const double ct = std::cos(t), st = std::sin(t), cf = std::cos(f), sf = std::sin(f), cp = std::cos(ps), sp = std::sin(ps);
+            se.s = view;                                                     // the camera looks along its +z axis
+            se.ex = make_float3(float(cp * ct * cf - sp * sf), float(cp * ct * sf + sp * cf), float(-cp * st));
+            se.ey = make_float3(float(-sp * ct * cf - cp * sf), float(-sp * ct * sf + cp * cf), float(sp * st));
+            se.cpos = make_float3(float(q.xpos * sc->dx * sc->nx), float(q.ypos * sc->dy * sc->ny), float(std::min(zg[nz], std::max(zg[0], q.zloc))));
+            se.cos_half_fov = float(std::cos(0.5 * std::min(q.qmax, 360.0) * M_PI / 180.0));
+            se.u_half = float(0.5 * q.umax * M_PI / 180.0); se.v_half = float(0.5 * q.vmax * M_PI / 180.0);
+            se.pix_per_u = float(q.nxr / (q.umax * M_PI / 180.0)); se.pix_per_v = float(q.nyr / (q.vmax * M_PI / 180.0));
+            se.ap2 = float(q.apsize * q.apsize);
+            se.inv_sz = 1.0f; se.inv_szs = 1.0f; se.zt = se.cpos.z; se.zref = 0.0f; se.lt = 0;
+            se.nxr = q.nxr; se.nyr = q.nyr; se.vertical_up = 0; se.fast_ok = 0;
+            se.off = off;
+            se.npix = double(sc->dx) * sc->nx * double(sc->dy) * sc->ny;
+            off += (long long)q.nxr * q.nyr;
+            continue;
+        }
         se.s = make_float3(view.x == 0.f ? 0.f : -view.x, view.y == 0.f ? 0.f : -view.y, -view.z);
         if (std::fabs(se.s.z) < 1e-3f) return fail(H, B200RT_ERR_ARG, "horizontal viewing direction is not supported");
         se.inv_sz = 1.0f / std::fabs(se.s.z);
@@ -1610,6 +1700,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
 
     H->k_pl = per_level; H->k_fz = (opt->solver != B200RT_SOLVER_3D);
+    H->k_cam = false;
+    for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
     H->pool_slots = opt->pool_slots;
     if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 96 && H->pool_slots != 128)
         return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 32, 64, 96 or 128");
@@ -1684,7 +1776,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     tpb = std::min(RT_TPB, std::max(32, (tpb / 32) * 32));
     const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz, np);
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
     const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4;
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -11,7 +11,8 @@ photons_per_set Nx Ny dx dy wvl_info sfc_2d solver`), the error strings.
 What is new (keyword-only, all optional): `seed` (reproducible Philox streams; default = wall clock like
 mcarats.py:432), `device`, `raw` (keep per-job fields instead of g-weighted per-run sums), `write_files` (emit the
 namelist text and MCARaTS-style .bin/.ctl outputs), `iz3l_fix`, `supervoxel`, `shard` / `reduce` (multi-GPU),
-`extra_sensors`, `solver_obj` (reuse a handle).
+`extra_sensors`, `solver_obj` (reuse a handle), `camera_pixels` (all-sky camera grid instead of the reference's fixed
+500 x 500).
 """
 
 import datetime
@@ -76,6 +77,7 @@ class mcarats_ng:
                  extra_sensors=None,
                  solver_obj=None,
                  wmin=None,
+                 camera_pixels=None,
                  dry_run=False):
 
         add_reference(self.reference)
@@ -115,6 +117,7 @@ class mcarats_ng:
         self.extra_sensors = list(extra_sensors) if extra_sensors else []
         self._solver_obj = solver_obj
         self._wmin = wmin
+        self.camera_pixels = camera_pixels
         self.dry_run = dry_run
         self.atm_1ds = atm_1ds
         self.atm_3ds = atm_3ds
@@ -336,11 +339,20 @@ class mcarats_ng:
             kw.update(sfc_type=int(n0['Sfc_mtype']), sfc_param=(float(n0['Sfc_param(1)']), 0.0, 0.0, 0.0, 0.0))
         sensors = []
         if self.target == 'radiance':
-            if int(n0.get('Rad_mrkind', 2)) != 2:
-                raise OSError('Error [mcarats_ng]: <sensor_type=%s> (Rad_mrkind=1, all-sky camera) is not implemented by the CUDA solver yet.' % self.sensor_type)
             nxr = int(n0.get('Rad_nxr', kw.get('nx', 1)))
             nyr = int(n0.get('Rad_nyr', kw.get('ny', 1)))
-            sensors.append(dict(kind=2, the=n0['Rad_the'], phi=n0['Rad_phi'], zloc=n0['Rad_zloc'], zref=n0.get('Rad_zref', DEFAULTS['Rad_zref']), nxr=nxr, nyr=nyr))
+            if int(n0.get('Rad_mrkind', 2)) == 1:
+                # all-sky camera (mcarats.py:291-296,369-371): local radiance per solid angle at (xpos, ypos, zloc)
+                if self.camera_pixels is not None:
+                    nxr, nyr = int(self.camera_pixels[0]), int(self.camera_pixels[1])
+                    for ig in range(self.Ng):
+                        self.nml[ig]['Rad_nxr'], self.nml[ig]['Rad_nyr'] = nxr, nyr
+                sensors.append(dict(kind=1, the=n0['Rad_the'], phi=n0['Rad_phi'], psi=n0.get('Rad_psi', DEFAULTS.get('Rad_psi', 0.0)),
+                                    zloc=n0['Rad_zloc'], nxr=nxr, nyr=nyr, xpos=n0.get('Rad_xpos', 0.5), ypos=n0.get('Rad_ypos', 0.5),
+                                    qmax=n0.get('Rad_qmax', 180.0), umax=n0.get('Rad_umax', DEFAULTS.get('Rad_umax', 180.0)),
+                                    vmax=n0.get('Rad_vmax', DEFAULTS.get('Rad_vmax', 180.0)), apsize=n0.get('Rad_apsize', 0.0)))
+            else:
+                sensors.append(dict(kind=2, the=n0['Rad_the'], phi=n0['Rad_phi'], zloc=n0['Rad_zloc'], zref=n0.get('Rad_zref', DEFAULTS['Rad_zref']), nxr=nxr, nyr=nyr))
             for e in self.extra_sensors:
                 sensors.append(dict(kind=2, the=180.0 - e['sensor_zenith_angle'], phi=cal_mca_azimuth(e['sensor_azimuth_angle']),
                                     zloc=e.get('sensor_altitude', n0['Rad_zloc']), zref=e.get('zref', 0.0), nxr=nxr, nyr=nyr))

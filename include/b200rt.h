@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 100 /* 0.1.0 */
+#define B200RT_VERSION 101 /* 0.1.1: b200rt_sensor grew the all-sky camera fields */
 
 /* error codes (0 = ok, negative = failure; message via b200rt_last_error) */
 enum {
@@ -58,14 +58,25 @@ enum { B200RT_TARGET_FLUX = 1, B200RT_TARGET_RADIANCE = 2, B200RT_TARGET_HEATING
 
 /* One radiance sensor (Rad_* of mcarats.py:285-307; docs er3t/rtm/mca/mca_inp.py:141-171,305-364).
  * kind 2 = "2nd kind": radiance averaged over the horizontal cross-section of a column,
- * parallel projection along the viewing vector; pixel = where the line of sight meets z = zref. */
+ * parallel projection along the viewing vector; pixel = where the line of sight meets z = zref.
+ * kind 1 = "1st kind" (all-sky camera, mcarats.py:291-296,369-371): local radiance at the point
+ * (xpos * Lx, ypos * Ly, zloc) averaged over the solid angle of each pixel; camera frame = Z-Y-Z rotation by
+ * (phi, the, psi), the camera looks along its +z axis (the, phi as for kind 2); field of view = cone of FULL
+ * angle qmax; polar pixel mapping (Rad_mpmap = 1): U = theta cos(az), V = theta sin(az) with U in
+ * [-umax/2, umax/2], V in [-vmax/2, vmax/2] (degrees) spread over nxr x nyr pixels. */
 typedef struct b200rt_sensor {
-    int32_t kind;       /* Rad_mrkind: 2 (satellite). 1 (all-sky camera) is not implemented yet */
+    int32_t kind;       /* Rad_mrkind: 2 (satellite) or 1 (all-sky camera)                      */
     int32_t nxr, nyr;   /* Rad_nxr, Rad_nyr                                                     */
     int32_t _pad;
     double  the, phi;   /* Rad_the (=180-vza), Rad_phi (=270-vaa): viewing vector               */
     double  zloc;       /* Rad_zloc: sensor altitude (m); >= TOA means "above the atmosphere"   */
     double  zref;       /* Rad_zref: reference level for pixel registration (m), default 0      */
+    /* kind 1 only */
+    double  psi;        /* Rad_psi: rotation about the camera axis (deg)                        */
+    double  xpos, ypos; /* Rad_xpos, Rad_ypos: relative position in the domain, 0 ... 1         */
+    double  qmax;       /* Rad_qmax: full angle of the field-of-view cone (deg)                 */
+    double  umax, vmax; /* Rad_umax, Rad_vmax: full angular width of the pixel grid (deg)       */
+    double  apsize;     /* Rad_apsize: aperture size (m): lower bound of the distance in 1/R^2  */
 } b200rt_sensor;
 
 /* The scene = everything that is identical for all (run, g) jobs (SURVEY.md Appendix B,

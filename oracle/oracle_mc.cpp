@@ -284,7 +284,13 @@ inline double brdf_eval(int type, const float* p, const V3& wi, const V3& wo) {
 }
 
 // ---------------------------------------------------------------- scene
-struct Sensor { V3 s; double zloc, zref; int nxr, nyr; };
+struct Sensor {
+    V3 s; double zloc, zref; int nxr, nyr;
+    // all-sky camera (Rad_mrkind = 1): `s` = viewing axis, (ex, ey) complete the camera frame (Z-Y-Z rotation by phi, the, psi)
+    int kind = 2;
+    V3 cpos{0, 0, 0}, ex{1, 0, 0}, ey{0, 1, 0};
+    double cos_half_fov = -1, u_half = PI / 2, v_half = PI / 2, ap2 = 0;
+};
 
 struct Scene {
     int nx, ny, nz, iz0 /*0-based first 3-D layer*/, nz3, np1d, np3d;
@@ -413,6 +419,47 @@ void local_estimate(const Scene& S, const JobCtx& J, const Tally& T, const Photo
                     Counters& C) {
     for (size_t k = 0; k < S.sens.size(); ++k) {
         const Sensor& se = S.sens[k];
+        if (se.kind == 1) {
+            // ---- all-sky camera: I_pix += w f exp(-tau) / (R^2 dOmega_pix) x (power per photon); nearest periodic image;
+            //      polar mapping U = theta cos(az), V = theta sin(az); dOmega = (sin(theta) / theta) dU dV
+            if (p.frozen) continue;
+            double dx = se.cpos.x - p.x, dy = se.cpos.y - p.y;
+            dx -= S.Lx * std::nearbyint(dx / S.Lx); dy -= S.Ly * std::nearbyint(dy / S.Ly);
+            const double dz = se.cpos.z - p.z;
+            const double R2 = dx * dx + dy * dy + dz * dz;
+            if (!(R2 > 1e-6) || std::fabs(dz) < 1e-3) continue;
+            const double R = std::sqrt(R2);
+            const V3 sd{dx / R, dy / R, dz / R};
+            if (std::fabs(sd.z) < 1e-4) continue;
+            const V3 v{-sd.x, -sd.y, -sd.z};
+            const double cq = dot(v, se.s);
+            if (cq < se.cos_half_fov) continue;
+            const double theta = std::acos(std::min(1.0, cq));
+            const double vx = dot(v, se.ex), vy = dot(v, se.ey), rho = std::sqrt(vx * vx + vy * vy);
+            const double U = rho > 0 ? theta * vx / rho : 0.0, V = rho > 0 ? theta * vy / rho : 0.0;
+            if (std::fabs(U) >= se.u_half || std::fabs(V) >= se.v_half) continue;
+            const int px = clampi(int((U + se.u_half) / (2 * se.u_half) * se.nxr), 0, se.nxr - 1);
+            const int py = clampi(int((V + se.v_half) / (2 * se.v_half) * se.nyr), 0, se.nyr - 1);
+            const double f = dens(sd);
+            if (f <= 0) continue;
+            int iz = p.iz;
+            if (sd.z > 0 && p.z >= S.z[iz + 1] && iz + 1 < S.nz) iz++;
+            if (sd.z < 0 && p.z <= S.z[iz] && iz > 0) iz--;
+            int ix = clampi(int(std::floor(p.x / S.dx)), 0, S.nx - 1), iy = clampi(int(std::floor(p.y / S.dy)), 0, S.ny - 1);
+            if (S.in3d(p.iz)) { ix = p.ix; iy = p.iy; }
+            const double tau = tau_to_level(S, J.abs1d, p.x, p.y, p.z, ix, iy, iz, sd, se.cpos.z, false, C.n_le_visit);
+            ++C.n_le;
+            const double sinc = theta > 1e-6 ? std::sin(theta) / theta : 1.0;
+            const double domega = sinc * (2 * se.u_half / se.nxr) * (2 * se.v_half / se.nyr);
+            const double contrib = wgt * f * std::exp(-tau) / (std::max(R2, se.ap2) * domega);
+            size_t off = 0;
+            for (size_t q = 0; q < k; ++q) off += size_t(S.sens[q].nxr) * S.sens[q].nyr;
+            size_t slabsz = 0;
+            for (auto& q : S.sens) slabsz += size_t(q.nxr) * q.nyr;
+            T.add(&T.rad[size_t(J.slab) * slabsz + off + size_t(py) * se.nxr + px], contrib * J.rscale * J.norm * S.Lx * S.Ly);
+            ++C.n_tally;
+            continue;
+        }
         const double ztop = S.z[S.nz], zbot = S.z[0];
         const double zt = std::min(ztop, std::max(zbot, se.zloc));
         const double dzs = (zt - p.z) / se.s.z;
@@ -733,7 +780,17 @@ int oracle_run(const b200rt_scene* sc, const b200rt_options* opt, const b200rt_j
         const V3 view = dir_from_angles(q.the, q.phi);
         Sensor se; se.s = V3{-view.x, -view.y, -view.z};
         if (se.s.x == 0) se.s.x = 0; if (se.s.y == 0) se.s.y = 0;   // no negative zeros
-        if (std::fabs(se.s.z) < 1e-6) return B200RT_ERR_ARG;
+        se.kind = q.kind;
+        if (q.kind == 1) {
+            const double t = q.the * DEG, f = q.phi * DEG, ps = q.psi * DEG;
+            const double ct = std::cos(t), st = std::sin(t), cf = std::cos(f), sf = std::sin(f), cp = std::cos(ps), sp = std::sin(ps);
+            se.s = view;
+            se.ex = V3{cp * ct * cf - sp * sf, cp * ct * sf + sp * cf, -cp * st};
+            se.ey = V3{-sp * ct * cf - cp * sf, -sp * ct * sf + cp * cf, sp * st};
+            se.cpos = V3{q.xpos * S.Lx, q.ypos * S.Ly, std::min(S.z[S.nz], std::max(S.z[0], q.zloc))};
+            se.cos_half_fov = std::cos(0.5 * std::min(q.qmax, 360.0) * DEG);
+            se.u_half = 0.5 * q.umax * DEG; se.v_half = 0.5 * q.vmax * DEG; se.ap2 = q.apsize * q.apsize;
+        } else if (std::fabs(se.s.z) < 1e-6) return B200RT_ERR_ARG;
         se.zloc = q.zloc; se.zref = q.zref; se.nxr = q.nxr; se.nyr = q.nyr;
         S.sens.push_back(se);
     }

@@ -77,7 +77,7 @@ def cloud_field(nx=16, ny=12, nz3=4, seed=2, dx=100.0, dz=200.0, zbase=600.0, cf
 
 
 def scene_3d(nx=16, ny=12, nz3=4, sza=40.0, saa_phi=200.0, sensors=None, sfc='lambert', seed=2, two_comp=False,
-             apf_mode='hg', dz3=200.0, zbase_layer=3, nlay=12, table=False, qmax=0.533133):
+             apf_mode='hg', dz3=200.0, zbase_layer=3, nlay=12, table=False, qmax=0.533133, clear_below=False):
     """
     Small 3-D cloud scene.  Atmosphere: `nlay` layers, non-uniform: fine (dz3) layers around the 3-D block.
     The 3-D block starts at 1-based layer `zbase_layer`.
@@ -94,6 +94,8 @@ def scene_3d(nx=16, ny=12, nz3=4, sza=40.0, saa_phi=200.0, sensors=None, sfc='la
     nz = z.size - 1
     ext1 = np.zeros((1, nz)); omg1 = np.ones((1, nz)); apf1 = -np.ones((1, nz))
     ext1[0] = rayleigh_ext(z, 0.05)
+    if clear_below:
+        ext1[0, :zbase_layer - 1] = 0.0      # nothing scatters next to a ground-based camera (bounded 1/R^2 variance)
     ext, omg, apf = cloud_field(nx, ny, nz3, seed=seed, apf_mode=apf_mode, dz=dz3)
     kw = {}
     if two_comp:

@@ -209,3 +209,30 @@ def test_cyclic_shift_invariance(solver):
     b = np.roll(b, (-sh[1], -sh[0]), axis=(1, 2))
     z, am, bm = zscores(a, b, nslab, (12, 16))
     assert_pixels(z, nslab)
+
+
+def test_3d_all_sky_camera(solver):
+    """Rad_mrkind = 1 (all-sky camera at the ground, looking up) next to a nadir satellite view in one launch: the point
+    detector's pixels are heavy-tailed, so the camera is compared through its mean over sky regions, the satellite
+    view pixel by pixel."""
+    npx = 12
+    sens = [dict(kind=1, the=0.0, phi=0.0, psi=30.0, zloc=0.0, nxr=npx, nyr=npx, xpos=0.4, ypos=0.6, qmax=150.0, umax=160.0, vmax=160.0, apsize=0.05),
+            dict(kind=2, the=180.0, phi=270.0, nxr=16, nyr=12)]
+    sc = scenes.scene_3d(sensors=sens, clear_below=True)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(400000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    gr, cr = g['rad'].reshape(nslab, -1), c['rad'].reshape(nslab, -1)
+    ncam = npx * npx
+    z, gm, cm = zscores(gr[:, ncam:], cr[:, ncam:], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    gcam, ccam = gr[:, :ncam].reshape(nslab, npx, npx), cr[:, :ncam].reshape(nslab, npx, npx)
+    assert np.all(np.isfinite(gcam)) and gcam.min() >= 0.0
+    # pixels outside the field-of-view cone stay empty on both sides
+    assert np.array_equal(gcam.sum(axis=0) == 0.0, ccam.sum(axis=0) == 0.0)
+    for sel in (np.s_[:, :], np.s_[: npx // 2, :], np.s_[npx // 2:, :], np.s_[:, : npx // 2], np.s_[:, npx // 2:]):
+        a, b = gcam[(slice(None),) + sel].mean(axis=(1, 2)), ccam[(slice(None),) + sel].mean(axis=(1, 2))
+        am, asem = scenes.mean_sem(a); bm, bsem = scenes.mean_sem(b)
+        assert abs(am / bm - 1.0) < 0.03 or abs(am - bm) < 3.5 * np.hypot(asem, bsem), (am, bm, asem, bsem)

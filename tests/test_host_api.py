@@ -100,8 +100,6 @@ def test_error_behaviour(inputs, tmp_path):
         run(inputs, tmp_path, atm_1ds=[])
     with pytest.raises(ValueError, match='Cannot ingest <surface_albedo>'):
         run(inputs, tmp_path, surface_albedo='bright')
-    with pytest.raises(OSError, match='all-sky'):
-        run(inputs, tmp_path, sensor_type='all-sky camera')
     with pytest.raises(OSError, match='Please provide both'):
         bmca.mca_out_ng()
     with pytest.raises(OSError):
@@ -119,3 +117,19 @@ def test_2d_surface_object(inputs, tmp_path):
     a = bmca.mca_out_ng(mca_obj=m, abs_obj=inputs['abs0']).data['rad']['data'].mean()
     b = bmca.mca_out_ng(mca_obj=m2, abs_obj=inputs['abs0']).data['rad']['data'].mean()
     assert abs(a / b - 1.0) < 0.05
+
+
+def test_all_sky_camera_through_the_public_api(inputs, tmp_path):
+    # sensor_type='all-sky camera': Rad_mrkind = 1, qmax = 178, apsize = 0.05, 500 x 500 pixels (er3t/rtm/mca/mcarats.py:291-296,369-371)
+    m = run(inputs, tmp_path, sensor_type='all-sky camera', sensor_zenith_angle=180.0, sensor_altitude=0.0, sensor_xpos=0.25, sensor_ypos=0.75,
+            camera_pixels=(10, 8), photons=3e4)
+    n = m.nml[0]
+    assert n['Rad_mrkind'] == 1 and n['Rad_qmax'] == 178.0 and n['Rad_apsize'] == 0.05 and n['Rad_xpos'] == 0.25 and n['Rad_ypos'] == 0.75
+    assert n['Rad_the'] == 0.0 and n['Rad_zloc'] == 0.0 and n['Rad_nxr'] == 10 and n['Rad_nyr'] == 8
+    se = m.scene.sensors[0]
+    assert se.kind == 1 and (se.nxr, se.nyr) == (10, 8) and se.qmax == 178.0 and se.xpos == 0.25
+    out = bmca.mca_out_ng(mca_obj=m, abs_obj=inputs['abs0'], mode='mean', squeeze=True).data
+    assert out['rad']['data'].shape == (10, 8) and np.all(np.isfinite(out['rad']['data'])) and out['rad']['data'].max() > 0.0
+    # without the override the reference's fixed 500 x 500 grid is what the namelist carries
+    m2 = run(inputs, tmp_path, sensor_type='all-sky camera', sensor_zenith_angle=180.0, sensor_altitude=0.0, dry_run=True)
+    assert m2.nml[0]['Rad_nxr'] == 500 and m2.nml[0]['Rad_nyr'] == 500

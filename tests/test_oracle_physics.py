@@ -174,3 +174,44 @@ def test_tabulated_phase_function_sampling_is_consistent_with_evaluation():
     g_sample = mu_s.mean()
     g_eval = 0.5 * np.trapezoid(p * mid, mid)
     assert abs(g_sample - g_eval) < 2e-3
+
+
+def test_all_sky_camera_matches_parallel_projection_sensors():
+    """Rad_mrkind = 1: in a plane-parallel atmosphere a ground camera looking up must record the same downward radiance
+    field that 2nd-kind sensors (parallel projection, domain average) placed at the ground report for the same viewing
+    vectors -- two independent estimators (1/R^2 point detector vs area average) in the SAME run.  Compared as
+    azimuthal means over two rings of zenith angle (the point detector is noisy pixel by pixel).  The layer next to
+    the camera is empty so that its estimator has bounded variance."""
+    z = np.arange(0.0, 12001.0, 1000.0)
+    nz = z.size - 1
+    ext = np.zeros((2, nz)); omg = np.ones((2, nz)); apf = np.zeros((2, nz))
+    ext[0] = scenes.rayleigh_ext(z, 0.2); apf[0] = -1.0
+    ext[0, 0] = 0.0
+    ext[1, 2] = 4.0 / 1000.0; apf[1, 2] = 0.8
+    npx = 36
+    rings = [(15.0, 10.0, 20.0, 6), (60.0, 50.0, 70.0, 12)]       # centre, inner, outer zenith angle (deg), azimuths
+    dirs = [(t, 360.0 * k / n + 7.0) for t, lo, hi, n in rings for k in range(n)]
+    sens = [dict(kind=1, the=0.0, phi=0.0, psi=0.0, zloc=0.0, nxr=npx, nyr=npx, xpos=0.5, ypos=0.5, qmax=178.0, umax=180.0, vmax=180.0, apsize=0.05)]
+    sens += [dict(kind=2, the=t, phi=f, zloc=0.0, nxr=1, nyr=1) for t, f in dirs]
+    sc = abi.HostScene(z, ext, omg, apf, dx=6.0e4, dy=6.0e4, sfc_type=1, sfc_param=(0.0, 0, 0, 0, 0), src_the=180.0 - 35.0, src_phi=270.0,
+                       sensors=sens)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(500000, nslab)
+    r = oracle.run(sc, opt, jobs)
+    rad = r['rad'].reshape(nslab, -1)
+    cam = rad[:, :npx * npx].reshape(nslab, npx, npx)            # [iy (V), ix (U)]
+    du = np.pi / npx
+    u = (np.arange(npx) + 0.5) * du - np.pi / 2
+    U, V = np.meshgrid(u, u, indexing='xy')
+    th = np.rad2deg(np.hypot(U, V))
+    k0 = 0
+    for t, lo, hi, n in rings:
+        sel = (th > lo) & (th < hi)
+        m_c, s_c = scenes.mean_sem(cam[:, sel].mean(axis=1))
+        m_p, s_p = scenes.mean_sem(rad[:, npx * npx + k0:npx * npx + k0 + n].mean(axis=1))
+        k0 += n
+        assert m_p > 0.05
+        assert abs(m_c / m_p - 1.0) < 0.08 or abs(m_c - m_p) < 3.5 * np.hypot(s_c, s_p), (t, m_c, m_p, s_c, s_p)
+    # the sun is seen at zenith angle 35 deg, azimuth 90 deg: that half of the sky is the brighter one
+    assert cam.mean(axis=0)[V > 0].mean() > 1.3 * cam.mean(axis=0)[V < 0].mean()
