@@ -147,6 +147,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--sv', type=str, default='0,0,0')
+    ap.add_argument('--empty-runs', type=int, default=0, help='A/B switch of the resident leg: -1 = no vertical merging of empty coarse cells')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -208,6 +209,7 @@ def main():
     sol = Solver(device=local)
     prep = mcarats_ng(**dict(kw, dry_run=True))
     jobs, keep = abi.make_jobs(**prep.jobs_args)
+    prep.options.empty_runs = args.empty_runs
     sol.upload_scene(prep.scene, prep.options)
     photons_step = int(np.sum(prep.jobs_args['nphot']))          # whole job set, all ranks
 
@@ -271,7 +273,7 @@ def main():
     d2h = int(8 * prep.scene.rad_size(prep.nslab))
     e2e = {'value': photons_step * esteps / dt, 'unit': 'photons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'steps': esteps, 'ms_per_step': 1e3 * dt / esteps,
-           'api': 'er3t_b200.rtm.mca.mcarats_ng(...) + mca_out_ng(...) with host numpy inputs (pageable memory)'}
+           'api': 'er3t_b200.rtm.mca.mcarats_ng(...) + mca_out_ng(...) with host numpy inputs (3-D fields page-locked by mca_atm_3d)'}
 
     if world > 1:
         torch.distributed.barrier()

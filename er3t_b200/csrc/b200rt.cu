@@ -83,7 +83,12 @@ struct DevScene {
     int nCx, nCy, shx, shy;   // coarse (emptiness) grid: 2^shx x 2^shy fine cells per coarse cell
     int flight_steps;         // max cell crossings per lane between two event phases
     int event_min;            // parked lanes that end the flight loop early
-    int regen_min;            // dead lanes that trigger a regeneration
+    // vertical runs of empty coarse cells (only when the 3-D layers are equally thick): a photon's fine z slab follows
+    // from its height by one multiply, so a box may span several coarse z groups
+    int uz_ok;                // 1: runs enabled, slab = uz_s0 + clamp(int((z - uz_z0) * uz_inv), 0, ncz - 1)
+    int uz_s0;                // index of the first fine slab of the 3-D block
+    float uz_z0, uz_inv;
+    float maj1d_blk;          // 1-D majorant of the whole 3-D block (used by boxes that span several groups)
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
     const float* e1tot;       // [nz]
@@ -186,13 +191,31 @@ __global__ void empty_kernel(const float* __restrict__ maj, int ncx, int ncy, in
     empty3[c] = m > 0.0f ? 0 : 1;
 }
 
-// fold the emptiness flag into the fine majorant grid: cells inside an empty coarse cell get a negative majorant
+// vertical runs of empty coarse cells, one thread per coarse column: runcode = first | last << 12 (z group numbers) of
+// the maximal run of empty coarse cells that contains the cell (a run of one when `merge` is off)
+__global__ void run_kernel(const unsigned char* __restrict__ empty3, int nCx, int nCy, int nCz, int gid0, int merge,
+                           int* __restrict__ runcode) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncol = nCx * nCy;
+    if (col >= ncol) return;
+    for (int K = 0; K < nCz;) {
+        if (!empty3[size_t(K) * ncol + col]) { runcode[size_t(K) * ncol + col] = -1; ++K; continue; }
+        int E = K + 1;
+        if (merge) while (E < nCz && empty3[size_t(E) * ncol + col]) ++E;
+        for (int q = K; q < E; ++q) runcode[size_t(q) * ncol + col] = (gid0 + K) | ((gid0 + E - 1) << 12);
+        K = E;
+    }
+}
+
+// fold the emptiness flag into the fine majorant grid: cells inside an empty coarse cell get the negative value
+// -(1 + runcode), exactly representable (24 bits), so that ONE look-up gives either the majorant or the empty box
 __global__ void mark_empty_kernel(float* __restrict__ maj, int ncx, int ncy, int ncz, int shx, int shy, int nCx, int nCy,
-                                  const int* __restrict__ fine2coarse_z, const unsigned char* __restrict__ empty3) {
+                                  const int* __restrict__ fine2coarse_z, const int* __restrict__ runcode) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncx * ncy * ncz) return;
     const int cix = c % ncx, ciy = (c / ncx) % ncy, ciz = c / (ncx * ncy);
-    if (empty3[(fine2coarse_z[ciz] * nCy + (ciy >> shy)) * nCx + (cix >> shx)]) maj[c] = -1.0f;
+    const int code = runcode[(size_t(fine2coarse_z[ciz]) * nCy + (ciy >> shy)) * nCx + (cix >> shx)];
+    if (code >= 0) maj[c] = -float(1 + code);
 }
 
 __global__ void tau_up_kernel(const float* __restrict__ ext3tot, const float* __restrict__ zgrd, int iz0, int nx, int ny,
@@ -700,9 +723,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
     const int nxy = S.nx * S.ny;
 
     unsigned n_cell = 0;
-    bool exhausted = false;
     // queue lengths (warp-uniform): DEAD, FLY, TENTATIVE (+ escapes), COLLISION, SURFACE.  Queues are LIFO stacks of slot numbers.
+    // Once the photon counter is exhausted nD becomes a large negative number: the dead queue never wins again and is no
+    // longer written.
     int nD = NP, nF = 0, nE = 0, nC = 0, nS = 0;
+    const int ND_DONE = -(1 << 29);
 
 #define RNG4(out)                                                                                              \
     {                                                                                                          \
@@ -718,12 +743,18 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         if (cond) (q)[(cnt) + __popc(m_ & lt_mask)] = (unsigned short)(val);   \
         (cnt) += __popc(m_);                                                  \
     }
+// the dead queue: not written once the photon source is exhausted (nD < 0)
+#define QPUSH_DEAD(cond, val)                                                          \
+    {                                                                                  \
+        const unsigned m_ = __ballot_sync(FULL, (cond));                               \
+        if ((cond) && nD >= 0) qD[nD + __popc(m_ & lt_mask)] = (unsigned short)(val);   \
+        nD += __popc(m_);                                                              \
+    }
 
     for (;;) {
         // =========================================================== pick the fullest queue
         __syncwarp();
-        const int nDe = exhausted ? 0 : nD;
-        int phase = 0, nbest = nDe;
+        int phase = 0, nbest = nD;
         if (nF >= nbest) { phase = 1; nbest = nF; }
         if (nE >= nbest) { phase = 2; nbest = nE; }
         if (nC >= nbest) { phase = 3; nbest = nC; }
@@ -740,7 +771,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)n);
             base = __shfl_sync(FULL, base, 0);
-            if (base + (unsigned long long)n >= S.nphot_local) exhausted = true;
+            const bool exhausted = base + (unsigned long long)n >= S.nphot_local;
             const unsigned long long idx = base + (unsigned long long)lane;
             const bool born = have && idx < S.nphot_local;
             if (born) {
@@ -775,7 +806,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
             QPUSH(qF, nF, born, slot);
-            QPUSH(qD, nD, have && !born, slot);
+            if (exhausted) nD = ND_DONE;
+            else QPUSH_DEAD(have && !born, slot);
             continue;
         }
 
@@ -809,6 +841,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
                 if (have && ev == EV_NONE) {
+                    if (!PL && S.uz_ok && (p.flags & FL_STALE)) {
+                        // left a box of several fine slabs sideways: the slab follows from the height
+                        p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
+                        p.flags &= ~FL_STALE;
+                    }
                     float4 A = sm.slabA[p.is];                  // zlo, zhi, 1-D majorant, bits: cz | group << 16 (< 0: 1-D slab)
                     int aw = __float_as_int(A.w);
                     bool in3 = aw >= 0;
@@ -816,6 +853,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     float mj = -1.0f;
                     if (in3) { mj = __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix); ++n_cell; }
                     if (!PL && mj >= 0.0f && (p.flags & FL_STALE)) {
+                        // (3-D layers of unequal thickness only; boxes never span more than one z group then)
                         // entered a non-empty coarse cell sideways: find the fine z slab of the current height
                         const int gw = __float_as_int(sm.grpA[(aw >> 16) & 0x7fff].w);
                         int lo = gw & 0xffff, hi = int(unsigned(gw) >> 16) - 1;
@@ -827,16 +865,21 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         A = sm.slabA[lo]; aw = __float_as_int(A.w);
                         mj = fmaxf(0.0f, __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix));
                     }
-                    const float4 G = sm.grpA[(aw >> 16) & 0x7fff];    // zlo, zhi, 1-D majorant of the group, bits: slo | shi << 16
                     const bool empty = mj < 0.0f;                       // 1-D slabs count as empty
+                    // empty boxes span the z groups glo ... ghi: the run of empty coarse cells encoded in the look-up
+                    // (3-D block), or the slab's own group
+                    const int grp = (aw >> 16) & 0x7fff;
+                    const int code = (in3 && empty) ? __float2int_rn(-mj) - 1 : (grp | (grp << 12));
+                    const int glo = code & 0xfff, ghi = (code >> 12) & 0xfff;
+                    const float4 G = sm.grpA[glo], Gh = sm.grpA[ghi];  // zlo, zhi, 1-D majorant of the group, bits: slo | shi << 16
                     // box in cell units: the fine cell, the enclosing coarse cell, or the whole domain (1-D slabs)
                     const int mx = in3 ? (empty ? cmx : 0) : 0x3fffffff, my = in3 ? (empty ? cmy : 0) : 0x3fffffff;
                     const int bxlo = p.cix & ~mx, bylo = p.ciy & ~my;
                     const int fxi = bxlo + ((mx + 1) & upmx), fyi = bylo + ((my + 1) & upmy);    // face index ahead
                     const float fxf = fminf(float(fxi), Lux), fyf = fminf(float(fyi), Luy);
-                    const float zf = upz ? (empty ? G.y : A.y) : (empty ? G.x : A.x);
+                    const float zf = upz ? (empty ? Gh.y : A.y) : (empty ? G.x : A.x);
                     const float tx = (fxf - ux) * kx, ty = (fyf - uy) * ky, tz = (zf - p.z) * kz;
-                    const float M = empty ? G.z : A.z + mj;
+                    const float M = empty ? (glo == ghi ? G.z : S.maj1d_blk) : A.z + mj;
                     const float dexit = fmaxf(0.0f, fminf(tz, fminf(tx, ty)));
                     const bool hit = p.tau < M * dexit;
                     const float dmove = hit ? __fdividef(p.tau, M) : dexit;
@@ -873,11 +916,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     p.cix = xc ? cxn : cxi; ux = xc ? uxn : ux;
                     p.ciy = yc ? cyn : cyi; uy = yc ? uyn : uy;
 
-                    const int gw = __float_as_int(G.w);
-                    const int slo = empty ? (gw & 0xffff) : p.is, shi = empty ? int(unsigned(gw) >> 16) : p.is + 1;
+                    const int slo = empty ? (__float_as_int(G.w) & 0xffff) : p.is;
+                    const int shi = empty ? int(unsigned(__float_as_int(Gh.w)) >> 16) : p.is + 1;
                     int fl = p.flags;
                     if (mj >= 0.0f) fl &= ~FL_STALE;                              // only a non-empty cell resolves staleness
-                    if ((xc || yc) && shi - slo > 1) fl |= FL_STALE;
+                    if ((xc || yc) && in3 && shi - slo > 1) fl |= FL_STALE;
                     if (hit) {
                         // park at the tentative collision point; RNG, voxel look-up and the layer search happen in the
                         // event phase
@@ -944,9 +987,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 RNG4(u);
                 {
                     // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
+                    const bool by_height = !PL && S.uz_ok && ev_empty && ev_in3;     // the box may span several z groups
+                    if (by_height) p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
                     const int4 sb = sm.slabB[p.is];
                     int l0 = sb.x, l1 = sb.y;
-                    if (ev_empty) { const int4 gb = sm.grpB[sb.z]; l0 = gb.z; l1 = gb.w; }
+                    if (ev_empty && !by_height) { const int4 gb = sm.grpB[sb.z]; l0 = gb.z; l1 = gb.w; }
                     p.iz = (l1 - l0 > 1) ? find_layer(sm, l0, l1, p.z) : l0;
                 }
                 const int izn = p.iz;
@@ -1022,7 +1067,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             if (accepted) pool_store_accept<NP>(pool, slot, p, c_apf, c_uz, c_uw, c_s3);
             QPUSH(qF, nF, rejected, slot);
             QPUSH(qC, nC, accepted, slot);
-            QPUSH(qD, nD, have && !rejected && !accepted, slot);
+            QPUSH_DEAD(have && !rejected && !accepted, slot);
             continue;
         }
 
@@ -1170,10 +1215,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 
         if (have && alive) pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
         QPUSH(qF, nF, have && alive, slot);
-        QPUSH(qD, nD, have && !alive, slot);
+        QPUSH_DEAD(have && !alive, slot);
     }
 #undef RNG4
 #undef QPUSH
+#undef QPUSH_DEAD
 
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
     unsigned long long c[9] = {CNT(CNT_PHOT), n_cell, CNT(CNT_TENT), CNT(CNT_COLL), CNT(CNT_SFC), CNT(CNT_LE), CNT(CNT_VISIT),
@@ -1267,7 +1313,7 @@ struct Handle {
     bool k_pl = false, k_fz = false, k_cam = false;
     // owned device memory
     std::vector<DevBuf*> pool;
-    DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3;
+    DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3, runcode;
     DevBuf st_e, st_o, st_a, f2c;
     DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
     DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
@@ -1370,7 +1416,7 @@ int b200rt_destroy(void* handle) {
     if (!H) return B200RT_ERR_ARG;
     cudaSetDevice(H->device);
     DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
-                     &H->st_e, &H->st_o, &H->st_a, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3,
+                     &H->st_e, &H->st_o, &H->st_a, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3, &H->runcode,
                      &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
                      &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
                      &H->flux, &H->rad, &H->heat};
@@ -1449,7 +1495,6 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     if (per_level) { shx = 0; shy = 0; cmz = 1; }
     S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 16;
     S.event_min = opt->event_min > 0 ? opt->event_min : 12;
-    S.regen_min = opt->regen_min > 0 ? opt->regen_min : 8;
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
@@ -1513,6 +1558,24 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         for (int K = 0; K + 1 < int(gz_lo.size()); ++K) for (int q = gz_lo[K]; q < gz_lo[K + 1]; ++q) f2c[q] = K;
         S.ngroup = int(g_cz.size());
     }
+    // vertical runs of empty coarse cells need "slab from height" in O(1): 3-D layers of equal thickness, targets that do
+    // not tally every level, and group numbers that fit the 12-bit run code
+    int gid3_0 = 0;
+    S.uz_ok = 0; S.uz_s0 = 0; S.uz_z0 = 0.f; S.uz_inv = 0.f; S.maj1d_blk = 0.f;
+    if (nz3 > 0) {
+        for (int g = 0; g < S.ngroup; ++g) if (g_cz[g] == 0) gid3_0 = g;
+        for (int g = 0; g < S.ngroup; ++g) if (g_cz[g] >= 0) S.maj1d_blk = std::max(S.maj1d_blk, g_maj1d[g]);
+        const double dz0 = zg[iz0 + 1] - zg[iz0];
+        bool uniform = true;
+        for (int k = 0; k < nz3; ++k) if (std::fabs((zg[iz0 + k + 1] - zg[iz0 + k]) - dz0) > 1e-5 * dz0) uniform = false;
+        for (int s = 0; s < S.nslab_z; ++s) if (czv[s] == 0) S.uz_s0 = s;
+        if (uniform && !per_level && opt->empty_runs >= 0) {
+            S.uz_ok = 1;
+            S.uz_z0 = float(zg[iz0]);
+            S.uz_inv = float(1.0 / (dz0 * svz));
+        }
+    }
+    if (S.ngroup > 4095) return fail(H, B200RT_ERR_ARG, "too many z groups for the packed run code (4095)");
     if ((rc = upload(H, H->zgrd, fz)) || (rc = upload(H, H->e1tot, fe1tot)) || (rc = upload(H, H->e1cum, fe1cum)) ||
         (rc = upload(H, H->e1, fe1)) || (rc = upload(H, H->o1, fo1)) || (rc = upload(H, H->a1, fa1)) ||
         (rc = upload(H, H->slab_lay0, lay0)) || (rc = upload(H, H->slab_cz, czv)) || (rc = upload(H, H->slab_maj1d, maj1d)) ||
@@ -1535,7 +1598,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         const size_t nvox = size_t(nz3) * sc->ny * sc->nx;
         const size_t nall = nvox * sc->np3d;
         if ((rc = dev_alloc(H, H->ext3tot, nvox * 4)) || (rc = dev_alloc(H, H->prop3, nall * 8)) ||
-            (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->empty3, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1))) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
+            (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->empty3, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1))) ||
+            (rc = dev_alloc(H, H->runcode, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1) * 4)) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
             (rc = dev_alloc(H, H->flag, 16)))
             return rc;
         // stage the caller's arrays on the device when they are host pointers (staging buffers are kept by the handle
@@ -1566,8 +1630,10 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         const int nC = S.nCx * S.nCy * int(gz_lo.size() - 1);
         empty_kernel<<<(nC + 127) / 128, 128>>>((const float*)H->maj.p, S.ncx, S.ncy, shx, shy, S.nCx, S.nCy, int(gz_lo.size() - 1),
                                                  (const int*)H->gz_lo.p, (unsigned char*)H->empty3.p);
+        run_kernel<<<(S.nCx * S.nCy + 127) / 128, 128>>>((const unsigned char*)H->empty3.p, S.nCx, S.nCy, int(gz_lo.size() - 1), gid3_0, S.uz_ok,
+                                                          (int*)H->runcode.p);
         mark_empty_kernel<<<(ncell + 127) / 128, 128>>>((float*)H->maj.p, S.ncx, S.ncy, S.ncz, shx, shy, S.nCx, S.nCy, (const int*)H->f2c.p,
-                                                          (const unsigned char*)H->empty3.p);
+                                                          (const int*)H->runcode.p);
         const int ncol = sc->nx * sc->ny;
         tau_up_kernel<<<(ncol + 127) / 128, 128>>>((const float*)H->ext3tot.p, S.zgrd, iz0, sc->nx, sc->ny, nz3, (float*)H->tu3.p);
         CK(cudaGetLastError());

@@ -140,7 +140,8 @@ typedef struct b200rt_options {
     int32_t cmx, cmy, cmz;        /* coarse (empty-space) cell in fine cells (x, y: power of two); 0 = auto */
     int32_t flight_steps;         /* max cell crossings per lane in one flight phase; 0 = auto      */
     int32_t event_min;            /* lanes parked at an event that end a flight phase early; 0 = auto */
-    int32_t regen_min;            /* reserved (was: dead lanes of a warp that trigger a regeneration) */
+    int32_t empty_runs;           /* vertical merging of empty coarse cells into one box: 0 = auto (on when the 3-D
+                                     layers are equally thick and no per-level tally is asked for), -1 = off        */
     int32_t pool_slots;           /* photon slots per warp in shared memory: 32, 64, 96, 128; 0 = auto */
     int32_t iso_ss;               /* Pho_iso_SS: partial-3D switches to 1-D after this order   */
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */

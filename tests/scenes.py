@@ -86,8 +86,9 @@ def scene_3d(nx=16, ny=12, nz3=4, sza=40.0, saa_phi=200.0, sensors=None, sfc='la
     z = [0.0]
     for i in range(zbase_layer - 1):
         z.append(z[-1] + 300.0)
+    dz3s = np.broadcast_to(np.asarray(dz3, dtype=np.float64), (nz3,))      # a scalar, or one thickness per 3-D layer
     for i in range(nz3):
-        z.append(z[-1] + dz3)
+        z.append(z[-1] + float(dz3s[i]))
     while len(z) < nlay + 1:
         z.append(z[-1] + 1500.0)
     z = np.array(z)
@@ -96,7 +97,7 @@ def scene_3d(nx=16, ny=12, nz3=4, sza=40.0, saa_phi=200.0, sensors=None, sfc='la
     ext1[0] = rayleigh_ext(z, 0.05)
     if clear_below:
         ext1[0, :zbase_layer - 1] = 0.0      # nothing scatters next to a ground-based camera (bounded 1/R^2 variance)
-    ext, omg, apf = cloud_field(nx, ny, nz3, seed=seed, apf_mode=apf_mode, dz=dz3)
+    ext, omg, apf = cloud_field(nx, ny, nz3, seed=seed, apf_mode=apf_mode, dz=float(np.mean(dz3)))
     kw = {}
     if two_comp:
         rng = np.random.default_rng(seed + 100)

@@ -139,6 +139,24 @@ def test_3d_supervoxel_sizes_agree_with_exact_traversal(solver, sv, cm, K):
     assert mean_close(g['rad'], c['rad'], nslab)
 
 
+@pytest.mark.parametrize('sv,cm,runs,uniform', [((1, 1, 1), (1, 1, 1), 0, True), ((2, 2, 1), (2, 2, 2), 0, True), ((2, 2, 3), (4, 4, 1), 0, True),
+                                                ((1, 1, 2), (2, 2, 2), -1, True), ((2, 2, 1), (2, 2, 2), 0, False), ((1, 1, 1), (1, 1, 3), 0, False)])
+def test_3d_empty_runs_tall_block(solver, sv, cm, runs, uniform):
+    """A 10-layer 3-D block with ragged cloud tops: boxes that merge vertical runs of empty coarse cells (3-D layers of
+    equal thickness, `empty_runs` = 0) against the one-group boxes (`empty_runs` = -1, or layers of unequal thickness,
+    which fall back to the layer search) -- all must reproduce the oracle's exact traversal."""
+    dz3 = 100.0 if uniform else np.array([60.0, 140.0, 100.0, 80.0, 120.0, 100.0, 90.0, 110.0, 100.0, 100.0])
+    sc = scenes.scene_3d(nz3=10, dz3=dz3, nlay=18, sza=50.0, sensors=[dict(the=180.0, phi=270.0, nxr=16, nyr=12)])
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2, sv=sv, cm=cm, empty_runs=runs)
+    jobs, keep = scenes.multi_seed_jobs(200000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    z, gm, cm_ = zscores(g['rad'], c['rad'], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    assert mean_close(g['rad'], c['rad'], nslab)
+
+
 def test_3d_oblique_multi_sensor(solver):
     sens = [dict(the=180.0, phi=270.0, nxr=16, nyr=12),
             dict(the=180.0 - 35.0, phi=30.0, nxr=16, nyr=12),

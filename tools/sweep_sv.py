@@ -23,7 +23,7 @@ for cfg in configs:
     m = mcarats_ng(**dict(kw, dry_run=True, supervoxel=sv))
     m.options.cmx, m.options.cmy, m.options.cmz = cm
     m.options.flight_steps = K
-    m.options.event_min, m.options.regen_min = E, R
+    m.options.event_min = E
     m.options.threads_per_block = tpb
     m.options.blocks_per_sm = bps
     jobs, keep = abi.make_jobs(**m.jobs_args)
