@@ -63,7 +63,7 @@ class Options(C.Structure):
                 ('cmx', C.c_int32), ('cmy', C.c_int32), ('cmz', C.c_int32), ('flight_steps', C.c_int32),
                 ('event_min', C.c_int32), ('empty_runs', C.c_int32), ('pool_slots', C.c_int32),
                 ('iso_ss', C.c_int32), ('iso_max', C.c_int32),
-                ('threads_per_block', C.c_int32), ('blocks_per_sm', C.c_int32),
+                ('threads_per_block', C.c_int32), ('blocks_per_sm', C.c_int32), ('smem_tally', C.c_int32),
                 ('wmin', C.c_double), ('wfac', C.c_double)]
 
 
@@ -300,7 +300,7 @@ def make_jobs(nphot, seeds, slabs, abs1d=None, flx_scale=None, rad_scale=None):
 
 def make_options(solver=SOLVER_3D, target=TARGET_FLUX, nslab=1, shard_rank=0, shard_world=1,
                  sv=(0, 0, 0), iso_ss=1, iso_max=0, wmin=0.2, wfac=1.0, threads_per_block=0, blocks_per_sm=0,
-                 cm=(0, 0, 0), flight_steps=0, event_min=0, empty_runs=0, pool_slots=0):
+                 cm=(0, 0, 0), flight_steps=0, event_min=0, empty_runs=0, pool_slots=0, smem_tally=0):
     o = Options()
     o.solver, o.target, o.nslab = int(solver), int(target), int(nslab)
     o.shard_rank, o.shard_world = int(shard_rank), int(shard_world)
@@ -309,6 +309,7 @@ def make_options(solver=SOLVER_3D, target=TARGET_FLUX, nslab=1, shard_rank=0, sh
     o.flight_steps = int(flight_steps)
     o.event_min, o.empty_runs = int(event_min), int(empty_runs)
     o.pool_slots = int(pool_slots)
+    o.smem_tally = int(smem_tally)
     o.iso_ss, o.iso_max = int(iso_ss), int(iso_max)
     o.threads_per_block, o.blocks_per_sm = int(threads_per_block), int(blocks_per_sm)
     o.wmin, o.wfac = float(wmin), float(wfac)

@@ -89,6 +89,9 @@ struct DevScene {
     int uz_s0;                // index of the first fine slab of the 3-D block
     float uz_z0, uz_inv;
     float maj1d_blk;          // 1-D majorant of the whole 3-D block (used by boxes that span several groups)
+    // small flux / heating tallies (plane-parallel and few-column scenes) are kept per block in shared memory and flushed
+    // once: all photons would otherwise hammer the same few L2 addresses
+    int ntal_flux_smem, ntal_heat_smem;   // doubles of the whole flux / heating tally held in shared memory (0: global atomics)
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
     const float* e1tot;       // [nz]
@@ -254,6 +257,8 @@ struct Smem {
     const float4* grpA;   // [ngroup]    (zlo, zhi, 1-D majorant, bits: first fine slab | one-past-last fine slab << 16)
     const int4* grpB;     // [ngroup]    (first fine slab, one-past-last fine slab, first layer, one-past-last layer)
     double* acc;          // per-thread energy accumulators [4][blockDim]: toa, sfc, atm, roulette
+    double* ftal;         // block-private flux tally (same layout as the global one) or nullptr
+    double* htal;         // block-private heating tally or nullptr
     unsigned* cnt;        // per-thread event counters [8][blockDim]
 };
 enum { ACC_TOA = 0, ACC_SFC = 1, ACC_ATM = 2, ACC_RR = 3 };
@@ -381,6 +386,10 @@ __device__ __forceinline__ float wrapf(float x, float L, float invL) {
 }
 
 __device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void tally_add_shared(double* p, double v) {
+    const unsigned a = unsigned(__cvta_generic_to_shared(p));
+    asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
 
 // column of the atmosphere grid a tally goes to
 __device__ __forceinline__ void tally_col(const DevScene& S, const Photon& p, int& fx, int& fy) {
@@ -391,32 +400,36 @@ __device__ __forceinline__ void tally_col(const DevScene& S, const Photon& p, in
     }
 }
 
-__device__ __noinline__ void flux_tally_at(const DevScene& S, int job, int fscale, float w, int fx, int fy, int var, int lev) {
+__device__ __noinline__ void flux_tally_at(const DevScene& S, double* ftal, int job, int fscale, float w, int fx, int fy, int var, int lev) {
     const DevJob& J = S.jobs[job];
     const size_t nxy = size_t(S.nx) * S.ny;
     double sc = J.norm * double(nxy);
     if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + lev);
-    tally_add(S.flux + ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx, double(w) * sc);
+    const size_t idx = ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx;
+    if (ftal) tally_add_shared(ftal + idx, double(w) * sc);
+    else tally_add(S.flux + idx, double(w) * sc);
 }
 __device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
     int fx, fy;
     tally_col(S, p, fx, fy);
-    flux_tally_at(S, p.job, p.flags & FL_FSCALE, p.w, fx, fy, var, lev);
-    CNT(CNT_TALLY)++;
+    flux_tally_at(S, sm.ftal, p.job, p.flags & FL_FSCALE, p.w, fx, fy, var, lev);
+    if (!sm.ftal) CNT(CNT_TALLY)++;          // counts updates that reach global memory; block-private ones are counted at the flush
 }
 
-__device__ __noinline__ void heat_tally_at(const DevScene& S, int job, int fscale, int fx, int fy, int iz, double dep) {
+__device__ __noinline__ void heat_tally_at(const DevScene& S, double* htal, int job, int fscale, int fx, int fy, int iz, double dep) {
     const DevJob& J = S.jobs[job];
     const size_t nxy = size_t(S.nx) * S.ny;
     double sc = J.norm * double(nxy);
     if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + iz);
-    tally_add(S.heat + (size_t(J.slab) * S.nz + iz) * nxy + size_t(fy) * S.nx + fx, dep * sc);
+    const size_t idx = (size_t(J.slab) * S.nz + iz) * nxy + size_t(fy) * S.nx + fx;
+    if (htal) tally_add_shared(htal + idx, dep * sc);
+    else tally_add(S.heat + idx, dep * sc);
 }
 __device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
     int fx, fy;
     tally_col(S, p, fx, fy);
-    heat_tally_at(S, p.job, p.flags & FL_FSCALE, fx, fy, iz, dep);
-    CNT(CNT_TALLY)++;
+    heat_tally_at(S, sm.htal, p.job, p.flags & FL_FSCALE, fx, fy, iz, dep);
+    if (!sm.htal) CNT(CNT_TALLY)++;
 }
 
 // layer that contains z among layers [l0, l1)
@@ -440,70 +453,112 @@ __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int 
     return fabsf(c2 - ca) * inv_absdz;
 }
 
-// exact traversal toward a sensor: layer by layer, column by column inside the 3-D block (oblique views, sensors
-// inside the atmosphere).  Kept out of line: it is the cold path of le_tau and large.  Everything is passed by value so
-// that the photon never has to live in local memory.
-struct RayTarget { float3 s; float zt; };   // unit direction of travel and the level at which the integral stops
+// Exact optical depth toward a sensor for oblique views and sensors inside the atmosphere.
+//   * 1-D extinction and gas absorption are horizontally uniform: their integral over the whole segment is a difference
+//     of the cumulative profiles, O(1) whatever the number of layers;
+//   * the 3-D extinction is integrated by an incremental voxel DDA (ray parameters of the next x / y / z face, one
+//     add per crossing) over the part of the segment inside the 3-D block only; the load of the next voxel is issued
+//     before the current one is consumed.
+// Kept out of line: it is the cold path of le_tau and large.  Everything is passed by value so that the photon never
+// has to live in local memory.
+struct RayTarget { float3 s; float zt; int lt; };   // unit direction of travel; level at which the integral stops and its layer
 __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __restrict__ smz, const float* __restrict__ sme1tot,
-                                             const RayTarget se, float x, float y, float z, int iz, int job, int has_abs,
-                                             int frozen, int fx, int fy, bool in3, unsigned* n_visit_out) {
-    const float* ab = S.job_abs + size_t(job) * S.nz;
+                                             const float* __restrict__ sme1cum, const RayTarget se, float x, float y, float z, int iz,
+                                             int job, int has_abs, int frozen, int fx, int fy, bool in3, unsigned* n_visit_out) {
+    const bool up = se.s.z > 0.0f;
+    const float isz = 1.0f / se.s.z;
+    // ---- 1-D part, closed form
+    float c_a = sme1cum[iz] + sme1tot[iz] * (z - smz[iz]);
+    float c_b = sme1cum[se.lt] + sme1tot[se.lt] * (se.zt - smz[se.lt]);
+    if (has_abs) {
+        const float* ab = S.job_abs + size_t(job) * S.nz;
+        const float* cb = S.job_cabs + size_t(job) * (S.nz + 1);
+        c_a += __ldg(cb + iz) + __ldg(ab + iz) * (z - smz[iz]);
+        c_b += __ldg(cb + se.lt) + __ldg(ab + se.lt) * (se.zt - smz[se.lt]);
+    }
+    float tau = fabsf((c_b - c_a) * isz);
+    *n_visit_out = 0;
+    if (S.nz3 <= 0) return tau;
+    // ---- 3-D part: the piece of [z, zt] inside the block
+    const float zb0 = smz[S.iz0], zb1 = smz[S.iz0 + S.nz3];
+    const float za = up ? fmaxf(z, zb0) : fminf(z, zb1);            // where the 3-D integral starts
+    const float ze = up ? fminf(se.zt, zb1) : fmaxf(se.zt, zb0);    // ... and ends
+    const float T = (ze - za) * isz;                                 // ray parameter (path length) of the 3-D piece
+    if (!(T > 0.0f)) return tau;
+    int l;                                                           // layer of the start point of the 3-D piece
+    if (za == z) {
+        l = min(S.iz0 + S.nz3 - 1, max(S.iz0, iz));
+        if (up && z >= smz[l + 1] && l + 1 < S.iz0 + S.nz3) l++;
+        if (!up && z <= smz[l] && l > S.iz0) l--;
+    } else l = up ? S.iz0 : S.iz0 + S.nz3 - 1;
     const int nxy = S.nx * S.ny;
     unsigned n_visit = 0;
-    float tau = 0.0f;
-    int l = iz;
-    const bool up = se.s.z > 0.0f;
-    if (up && z >= smz[l + 1] && l + 1 < S.nz) l++;
-    if (!up && z <= smz[l] && l > 0) l--;
-    bool have_col = (in3 && (l == iz)) || frozen;
-    const float isx = se.s.x != 0.0f ? 1.0f / se.s.x : RT_INF;
-    const float isy = se.s.y != 0.0f ? 1.0f / se.s.y : RT_INF;
-    const float isz = 1.0f / se.s.z;
-    for (;;) {
-        const float zb = up ? fminf(smz[l + 1], se.zt) : fmaxf(smz[l], se.zt);
-        const float dl = fmaxf(0.0f, (zb - z) * isz);
-        const float base = sme1tot[l] + (has_abs ? __ldg(ab + l) : 0.0f);
-        const bool l3 = (S.nz3 > 0) && l >= S.iz0 && l < S.iz0 + S.nz3;
-        if (!l3) {
-            tau += base * dl;
-            if (!frozen) { x = wrapf(x + se.s.x * dl, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * dl, S.Ly, S.inv_Ly); }
-            have_col = frozen;
-        } else if (frozen) {
-            tau += (base + __ldg(S.ext3tot + (l - S.iz0) * nxy + fy * S.nx + fx)) * dl;
+    if (frozen) {
+        // column-frozen photon: the ray stays in its column
+        const float* col = S.ext3tot + fy * S.nx + fx;
+        float zc = za;
+        for (;;) {
+            const float zn = up ? fminf(smz[l + 1], ze) : fmaxf(smz[l], ze);
+            tau += __ldg(col + (l - S.iz0) * nxy) * (zn - zc) * isz;
             ++n_visit;
+            zc = zn;
+            if (up) { if (zn >= ze || ++l >= S.iz0 + S.nz3) break; }
+            else { if (zn <= ze || --l < S.iz0) break; }
+        }
+        *n_visit_out = n_visit;
+        return tau;
+    }
+    if (za != z || !in3) {
+        const float d0 = (za - z) * isz;
+        x = wrapf(x + se.s.x * d0, S.Lx, S.inv_Lx); y = wrapf(y + se.s.y * d0, S.Ly, S.inv_Ly);
+        fx = min(S.nx - 1, max(0, int(x * S.inv_dx)));
+        fy = min(S.ny - 1, max(0, int(y * S.inv_dy)));
+    }
+    // ray parameters of the next faces, measured from the start of the 3-D piece
+    const bool px = se.s.x > 0.0f, py = se.s.y > 0.0f;
+    const float isx = se.s.x != 0.0f ? 1.0f / se.s.x : RT_INF, isy = se.s.y != 0.0f ? 1.0f / se.s.y : RT_INF;
+    float tmx = se.s.x != 0.0f ? fmaxf(0.0f, (float(fx + (px ? 1 : 0)) * S.dx - x) * isx) : RT_INF;
+    float tmy = se.s.y != 0.0f ? fmaxf(0.0f, (float(fy + (py ? 1 : 0)) * S.dy - y) * isy) : RT_INF;
+    const float tdx = se.s.x != 0.0f ? fabsf(S.dx * isx) : 0.0f, tdy = se.s.y != 0.0f ? fabsf(S.dy * isy) : 0.0f;
+    float tmz = fminf(T, ((up ? smz[l + 1] : smz[l]) - za) * isz);
+    const int dl = up ? 1 : -1;
+    const int lend = up ? S.iz0 + S.nz3 : S.iz0 - 1;                 // first layer outside the block
+    const float* base = S.ext3tot;
+    int row = ((l - S.iz0) * S.ny + fy) * S.nx;                      // index of voxel (0, fy, l)
+    float t = 0.0f, tau3 = 0.0f;
+    float e = __ldg(base + row + fx);
+    for (;;) {
+        const float tn = fminf(fminf(tmx, tmy), tmz);
+        const float seg = tn - t;
+        t = tn;
+        ++n_visit;
+        bool done = tn >= T;
+        if (tmx <= tmy && tmx <= tmz) {
+            fx += px ? 1 : -1;
+            if (fx >= S.nx) fx = 0;
+            if (fx < 0) fx = S.nx - 1;
+            tmx += tdx;
+        } else if (tmy <= tmz) {
+            fy += py ? 1 : -1;
+            if (fy >= S.ny) fy = 0;
+            if (fy < 0) fy = S.ny - 1;
+            tmy += tdy;
+            row = ((l - S.iz0) * S.ny + fy) * S.nx;
         } else {
-            if (!have_col) {
-                fx = min(S.nx - 1, max(0, int(x * S.inv_dx)));
-                fy = min(S.ny - 1, max(0, int(y * S.inv_dy)));
-                have_col = true;
-            }
-            float rem = dl;
-            for (;;) {
-                float tx = RT_INF, ty = RT_INF;
-                if (se.s.x > 0.0f) tx = (float(fx + 1) * S.dx - x) * isx; else if (se.s.x < 0.0f) tx = (float(fx) * S.dx - x) * isx;
-                if (se.s.y > 0.0f) ty = (float(fy + 1) * S.dy - y) * isy; else if (se.s.y < 0.0f) ty = (float(fy) * S.dy - y) * isy;
-                tx = fmaxf(tx, 0.0f); ty = fmaxf(ty, 0.0f);
-                const float step = fminf(rem, fminf(tx, ty));
-                tau += (base + __ldg(S.ext3tot + (l - S.iz0) * nxy + fy * S.nx + fx)) * step;
-                ++n_visit;
-                if (step >= rem) { x += se.s.x * rem; y += se.s.y * rem; break; }
-                rem -= step;
-                x += se.s.x * step; y += se.s.y * step;
-                if (tx <= ty) {
-                    if (se.s.x > 0.0f) { fx++; x = float(fx) * S.dx; if (fx >= S.nx) { fx = 0; x = 0.0f; } }
-                    else { x = float(fx) * S.dx; fx--; if (fx < 0) { fx = S.nx - 1; x = S.Lx; } }
-                } else {
-                    if (se.s.y > 0.0f) { fy++; y = float(fy) * S.dy; if (fy >= S.ny) { fy = 0; y = 0.0f; } }
-                    else { y = float(fy) * S.dy; fy--; if (fy < 0) { fy = S.ny - 1; y = S.Ly; } }
-                }
+            l += dl;
+            if (l == lend) done = true;
+            else {
+                tmz = fminf(T, ((up ? smz[l + 1] : smz[l]) - za) * isz);
+                row = ((l - S.iz0) * S.ny + fy) * S.nx;
             }
         }
-        z = zb;
-        if (up) { if (zb >= se.zt || l + 1 >= S.nz) break; l++; }
-        else { if (zb <= se.zt || l == 0) break; l--; }
+        const float en = done ? 0.0f : __ldg(base + row + fx);      // next voxel: in flight while this one is consumed
+        tau3 = fmaf(e, seg, tau3);
+        if (done) break;
+        e = en;
     }
     *n_visit_out = n_visit;
-    return tau;
+    return tau + tau3;
 }
 
 // Optical depth (extinction + gas absorption) from the photon position along the sensor direction to the sensor's
@@ -537,8 +592,8 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
     }
     if (frozen) { fx = p.cix; fy = p.ciy; }
     unsigned nv = 0;
-    const RayTarget rt = {se.s, se.zt};
-    const float t = le_tau_generic(S, sm.z, sm.e1tot, rt, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
+    const RayTarget rt = {se.s, se.zt, se.lt};
+    const float t = le_tau_generic(S, sm.z, sm.e1tot, sm.e1cum, rt, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
     CNT(CNT_VISIT) += nv;
     return t;
 }
@@ -570,6 +625,7 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
 // Periodic domain: the nearest image of the camera is used.  Polar pixel mapping: U = theta cos(az), V = theta sin(az);
 // a pixel of size dU x dV subtends dOmega = (sin(theta) / theta) dU dV.
 __device__ __noinline__ float camera_le(const DevScene& S, const float* __restrict__ smz, const float* __restrict__ sme1tot,
+                                        const float* __restrict__ sme1cum,
                                         const DevSensor& se, float x, float y, float z, int iz, int job, int has_abs, int fx, int fy,
                                         bool in3, const float3 din, int evk, float apf, int sfc_type, float p0, float p1, float p2,
                                         float p3, float p4, int* pix_out, unsigned* n_visit_out) {
@@ -599,8 +655,8 @@ __device__ __noinline__ float camera_le(const DevScene& S, const float* __restri
     if (evk == EV_COLL) f = phase_eval(S.pt, apf, din.x * sdir.x + din.y * sdir.y + din.z * sdir.z) * (0.25f / RT_PI);
     else f = sdir.z > 0.0f ? brdf_eval(sfc_type, p0, p1, p2, p3, p4, make_float3(-din.x, -din.y, -din.z), sdir) * sdir.z : 0.0f;
     if (!(f > 0.0f)) return 0.0f;
-    const RayTarget rt = {sdir, se.cpos.z};
-    const float tau = le_tau_generic(S, smz, sme1tot, rt, x, y, z, iz, job, has_abs, 0, fx, fy, in3, n_visit_out);
+    const RayTarget rt = {sdir, se.cpos.z, se.lt};
+    const float tau = le_tau_generic(S, smz, sme1tot, sme1cum, rt, x, y, z, iz, job, has_abs, 0, fx, fy, in3, n_visit_out);
     const float sinc = theta > 1e-4f ? __sinf(theta) / theta : 1.0f;
     const float domega = sinc / (se.pix_per_u * se.pix_per_v);
     return f * __expf(-tau) / (fmaxf(R2, se.ap2) * domega);
@@ -675,7 +731,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         float4* grpA = q4; q4 += S.ngroup;
         int4* grpB = reinterpret_cast<int4*>(q4); q4 += S.ngroup;
         double* acc = reinterpret_cast<double*>(q4);
-        unsigned* cnt = reinterpret_cast<unsigned*>(acc + 4 * blockDim.x);
+        double* tal = acc + 4 * blockDim.x;
+        const int ntal = PL ? S.ntal_flux_smem + S.ntal_heat_smem : 0;
+        unsigned* cnt = reinterpret_cast<unsigned*>(tal + ntal);
         float* q = reinterpret_cast<float*>(cnt + 8 * blockDim.x);
         float* z = q; q += S.nz + 1;
         float* e1tot = q; q += S.nz;
@@ -707,6 +765,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             grpB[i] = make_int4(s0, s1, l0, l1);
         }
         for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
+        for (int i = threadIdx.x; i < ntal; i += blockDim.x) tal[i] = 0.0;
+        sm.ftal = (PL && S.ntal_flux_smem > 0) ? tal : nullptr;
+        sm.htal = (PL && S.ntal_heat_smem > 0) ? tal + S.ntal_flux_smem : nullptr;
         for (int k = 0; k < 8; ++k) cnt[k * blockDim.x + threadIdx.x] = 0u;
         for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
@@ -1148,7 +1209,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         int pix = 0;
                         unsigned nv = 0;
                         const bool in3 = (S.nz3 > 0) && p.iz >= S.iz0 && p.iz < S.iz0 + S.nz3;
-                        const float c = camera_le(S, sm.z, sm.e1tot, se, p.x, p.y, p.z, p.iz, p.job, p.flags & FL_ABS, fx, fy, in3, p.d, evk, apf,
+                        const float c = camera_le(S, sm.z, sm.e1tot, sm.e1cum, se, p.x, p.y, p.z, p.iz, p.job, p.flags & FL_ABS, fx, fy, in3, p.d, evk, apf,
                                                   sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], &pix, &nv);
                         CNT(CNT_VISIT) += nv;
                         if (c > 0.0f) {
@@ -1221,6 +1282,18 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #undef QPUSH
 #undef QPUSH_DEAD
 
+    // ---- flush the block-private tallies (one global atomic per non-zero entry and block)
+    if (PL && (sm.ftal || sm.htal)) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < S.ntal_flux_smem; i += blockDim.x) {
+            const double v = sm.ftal[i];
+            if (v != 0.0) { tally_add(S.flux + i, v); CNT(CNT_TALLY)++; }
+        }
+        for (int i = threadIdx.x; i < S.ntal_heat_smem; i += blockDim.x) {
+            const double v = sm.htal[i];
+            if (v != 0.0) { tally_add(S.heat + i, v); CNT(CNT_TALLY)++; }
+        }
+    }
     // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
     unsigned long long c[9] = {CNT(CNT_PHOT), n_cell, CNT(CNT_TENT), CNT(CNT_COLL), CNT(CNT_SFC), CNT(CNT_LE), CNT(CNT_VISIT),
                                CNT(CNT_TALLY), CNT(CNT_KILL)};
@@ -1728,6 +1801,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
             se.pix_per_u = float(q.nxr / (q.umax * M_PI / 180.0)); se.pix_per_v = float(q.nyr / (q.vmax * M_PI / 180.0));
             se.ap2 = float(q.apsize * q.apsize);
             se.inv_sz = 1.0f; se.inv_szs = 1.0f; se.zt = se.cpos.z; se.zref = 0.0f; se.lt = 0;
+            for (int i = 0; i < nz; ++i) if (se.zt >= fz[i]) se.lt = i;
             se.nxr = q.nxr; se.nyr = q.nyr; se.vertical_up = 0; se.fast_ok = 0;
             se.off = off;
             se.npix = double(sc->dx) * sc->nx * double(sc->dy) * sc->ny;
@@ -1765,6 +1839,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.flux = (double*)H->flux.p; S.rad = (double*)H->rad.p; S.heat = (double*)H->heat.p;
     S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
 
+    // block-private tallies when the whole flux + heating tally is small (plane-parallel / few-column scenes)
+    S.ntal_flux_smem = 0; S.ntal_heat_smem = 0;
+    if (per_level && H->nflux + H->nheat <= 2048 && opt->smem_tally >= 0) { S.ntal_flux_smem = int(H->nflux); S.ntal_heat_smem = int(H->nheat); }
     H->k_pl = per_level; H->k_fz = (opt->solver != B200RT_SOLVER_3D);
     H->k_cam = false;
     for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
@@ -1843,7 +1920,8 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
-    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4;
+    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
+                        8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 101 /* 0.1.1: b200rt_sensor grew the all-sky camera fields */
+#define B200RT_VERSION 102 /* 0.1.2: options.empty_runs (was reserved), options.smem_tally (was padding) */
 
 /* error codes (0 = ok, negative = failure; message via b200rt_last_error) */
 enum {
@@ -147,6 +147,8 @@ typedef struct b200rt_options {
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */
     int32_t threads_per_block;    /* 0 = auto                                                  */
     int32_t blocks_per_sm;        /* 0 = auto                                                  */
+    int32_t smem_tally;           /* block-private flux / heating tallies in shared memory when the whole tally is small
+                                     (<= 2048 doubles): 0 = auto (on), -1 = off (global atomics only)               */
     double  wmin;                 /* Pho_wmin: Russian roulette threshold (0 = no roulette)    */
     double  wfac;                 /* Pho_wfac: weight given to roulette survivors              */
 } b200rt_options;
