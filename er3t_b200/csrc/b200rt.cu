@@ -520,39 +520,35 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
     float tmx = se.s.x != 0.0f ? fmaxf(0.0f, (float(fx + (px ? 1 : 0)) * S.dx - x) * isx) : RT_INF;
     float tmy = se.s.y != 0.0f ? fmaxf(0.0f, (float(fy + (py ? 1 : 0)) * S.dy - y) * isy) : RT_INF;
     const float tdx = se.s.x != 0.0f ? fabsf(S.dx * isx) : 0.0f, tdy = se.s.y != 0.0f ? fabsf(S.dy * isy) : 0.0f;
-    float tmz = fminf(T, ((up ? smz[l + 1] : smz[l]) - za) * isz);
-    const int dl = up ? 1 : -1;
-    const int lend = up ? S.iz0 + S.nz3 : S.iz0 - 1;                 // first layer outside the block
+    // one branch-free step per voxel (lanes of a warp cross different faces; selects keep them in one instruction stream)
+    const int sx = px ? 1 : -1, sy = py ? 1 : -1, dl = up ? 1 : -1;
+    const float* zl = smz + S.iz0 + (up ? 1 : 0);                    // zl[k]: the face of block layer k ahead of the ray
+    int lz = l - S.iz0;
+    const int lzend = up ? S.nz3 : -1;                               // first layer outside the block
+    float tmz = fminf(T, (zl[lz] - za) * isz);
     const float* base = S.ext3tot;
-    int row = ((l - S.iz0) * S.ny + fy) * S.nx;                      // index of voxel (0, fy, l)
     float t = 0.0f, tau3 = 0.0f;
-    float e = __ldg(base + row + fx);
+    float e = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
     for (;;) {
         const float tn = fminf(fminf(tmx, tmy), tmz);
         const float seg = tn - t;
         t = tn;
         ++n_visit;
-        bool done = tn >= T;
-        if (tmx <= tmy && tmx <= tmz) {
-            fx += px ? 1 : -1;
-            if (fx >= S.nx) fx = 0;
-            if (fx < 0) fx = S.nx - 1;
-            tmx += tdx;
-        } else if (tmy <= tmz) {
-            fy += py ? 1 : -1;
-            if (fy >= S.ny) fy = 0;
-            if (fy < 0) fy = S.ny - 1;
-            tmy += tdy;
-            row = ((l - S.iz0) * S.ny + fy) * S.nx;
-        } else {
-            l += dl;
-            if (l == lend) done = true;
-            else {
-                tmz = fminf(T, ((up ? smz[l + 1] : smz[l]) - za) * isz);
-                row = ((l - S.iz0) * S.ny + fy) * S.nx;
-            }
-        }
-        const float en = done ? 0.0f : __ldg(base + row + fx);      // next voxel: in flight while this one is consumed
+        const bool cx = tmx <= tmy && tmx <= tmz;
+        const bool cy = !cx && tmy <= tmz;
+        const bool cz = !(cx || cy);
+        int nfx = fx + sx, nfy = fy + sy;
+        nfx = nfx >= S.nx ? 0 : (nfx < 0 ? S.nx - 1 : nfx);
+        nfy = nfy >= S.ny ? 0 : (nfy < 0 ? S.ny - 1 : nfy);
+        fx = cx ? nfx : fx;
+        fy = cy ? nfy : fy;
+        lz = cz ? lz + dl : lz;
+        tmx = cx ? tmx + tdx : tmx;
+        tmy = cy ? tmy + tdy : tmy;
+        const bool done = tn >= T || lz == lzend;
+        const int lzc = min(S.nz3 - 1, max(0, lz));
+        tmz = cz ? fminf(T, (zl[lzc] - za) * isz) : tmz;
+        const float en = done ? 0.0f : __ldg(base + (lzc * S.ny + fy) * S.nx + fx);   // next voxel: in flight while this one is consumed
         tau3 = fmaf(e, seg, tau3);
         if (done) break;
         e = en;
