@@ -65,6 +65,8 @@ struct DevJob {
     int has_abs;
     int has_fscale;
     int _pad;
+    unsigned long long flux_off;   // slab * 3 * (nz + 1) * nx * ny: start of the job's slab in the flux tally
+    unsigned long long heat_off;   // slab * nz * nx * ny
 };
 
 struct DevStats {
@@ -131,7 +133,7 @@ struct DevScene {
     const DevJob* jobs;
     const float* job_abs;     // [njob][nz]
     const float* job_cabs;    // [njob][nz+1]
-    const double* job_fscale; // [njob][nz+1]
+    const double* job_fscale; // [njob][nz+1]  norm * (columns in the domain) * per-level factor: the complete tally scale
     unsigned long long nphot_local;
     // outputs
     double* flux;
@@ -400,35 +402,29 @@ __device__ __forceinline__ void tally_col(const DevScene& S, const Photon& p, in
     }
 }
 
-__device__ __noinline__ void flux_tally_at(const DevScene& S, double* ftal, int job, int fscale, float w, int fx, int fy, int var, int lev) {
-    const DevJob& J = S.jobs[job];
-    const size_t nxy = size_t(S.nx) * S.ny;
-    double sc = J.norm * double(nxy);
-    if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + lev);
-    const size_t idx = ((size_t(J.slab) * 3 + var) * (S.nz + 1) + lev) * nxy + size_t(fy) * S.nx + fx;
-    if (ftal) tally_add_shared(ftal + idx, double(w) * sc);
-    else tally_add(S.flux + idx, double(w) * sc);
+// The out-of-line part of a flux / heating tally gets everything by value (the caller reads the scene from the constant
+// bank; a by-reference DevScene would turn every field into a dependent generic load): two independent loads (the
+// complete per-level scale, the slab offset of the job), one fp64 multiply, one atomic.
+__device__ __noinline__ void tally_at(double* base, int is_shared, const double* scale, const unsigned long long* slab_off,
+                                      unsigned long long rel, double w) {
+    const double v = w * __ldg(scale);
+    const size_t idx = size_t(__ldg(slab_off) + rel);
+    if (is_shared) tally_add_shared(base + idx, v);
+    else tally_add(base + idx, v);
 }
 __device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
     int fx, fy;
     tally_col(S, p, fx, fy);
-    flux_tally_at(S, sm.ftal, p.job, p.flags & FL_FSCALE, p.w, fx, fy, var, lev);
+    tally_at(sm.ftal ? sm.ftal : S.flux, sm.ftal != nullptr, S.job_fscale + p.job * (S.nz + 1) + lev, &S.jobs[p.job].flux_off,
+             (unsigned long long)(var * (S.nz + 1) + lev) * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx),
+             double(p.w));
     if (!sm.ftal) CNT(CNT_TALLY)++;          // counts updates that reach global memory; block-private ones are counted at the flush
-}
-
-__device__ __noinline__ void heat_tally_at(const DevScene& S, double* htal, int job, int fscale, int fx, int fy, int iz, double dep) {
-    const DevJob& J = S.jobs[job];
-    const size_t nxy = size_t(S.nx) * S.ny;
-    double sc = J.norm * double(nxy);
-    if (fscale) sc *= __ldg(S.job_fscale + size_t(job) * (S.nz + 1) + iz);
-    const size_t idx = (size_t(J.slab) * S.nz + iz) * nxy + size_t(fy) * S.nx + fx;
-    if (htal) tally_add_shared(htal + idx, dep * sc);
-    else tally_add(S.heat + idx, dep * sc);
 }
 __device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
     int fx, fy;
     tally_col(S, p, fx, fy);
-    heat_tally_at(S, sm.htal, p.job, p.flags & FL_FSCALE, fx, fy, iz, dep);
+    tally_at(sm.htal ? sm.htal : S.heat, sm.htal != nullptr, S.job_fscale + p.job * (S.nz + 1) + iz, &S.jobs[p.job].heat_off,
+             (unsigned long long)iz * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx), dep);
     if (!sm.htal) CNT(CNT_TALLY)++;
 }
 
@@ -1889,10 +1885,12 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
             }
             jcabs[size_t(j) * (nz + 1) + nz] = float(c);
         }
-        if (q.flx_scale) {
-            d.has_fscale = 1;
-            for (int i = 0; i <= nz; ++i) jfs[size_t(j) * (nz + 1) + i] = q.flx_scale[i];
-        }
+        // complete tally scale per level: normalisation x columns in the domain x the caller's per-level factor
+        const double nxy_d = double(S.nx) * double(S.ny);
+        for (int i = 0; i <= nz; ++i) jfs[size_t(j) * (nz + 1) + i] = d.norm * nxy_d * (q.flx_scale ? q.flx_scale[i] : 1.0);
+        if (q.flx_scale) d.has_fscale = 1;
+        d.flux_off = (unsigned long long)q.slab * 3ull * (unsigned long long)(nz + 1) * (unsigned long long)(S.nx) * (unsigned long long)(S.ny);
+        d.heat_off = (unsigned long long)q.slab * (unsigned long long)nz * (unsigned long long)(S.nx) * (unsigned long long)(S.ny);
     }
     int rc;
     if ((rc = upload(H, H->jobs, dj)) || (rc = upload(H, H->job_abs, jabs)) || (rc = upload(H, H->job_cabs, jcabs)) ||

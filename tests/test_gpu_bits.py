@@ -89,6 +89,24 @@ def test_every_photon_is_traced_once_and_shards_add_up(solver):
         assert again['stats'][k] == full['stats'][k]
 
 
+def test_block_private_tallies_equal_global_atomics(solver):
+    """Small flux / heating tallies are accumulated per block in shared memory and flushed once; the photon set is the
+    same (counter-based streams), so the result must equal the global-atomics path up to the summation order."""
+    sc, absg = scenes.plane_parallel(absorb=True, with_sensor=False)
+    jobs, keep = abi.make_jobs([150000, 50000, 30000], [5, 6, 7], [0, 1, 1], abs1d=[absg] * 3)
+    res = []
+    for st in (0, -1):
+        opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_HEATING, nslab=2, wmin=0.2, smem_tally=st)
+        solver.upload_scene(sc, opt); solver.run(jobs)
+        res.append(solver.results())
+    a, b = res
+    assert a['stats']['n_tally'] < b['stats']['n_tally'] / 100        # flushed entries vs one global atomic per crossing
+    assert np.allclose(a['flux'], b['flux'], rtol=1e-10, atol=1e-15)
+    assert np.allclose(a['heat'], b['heat'], rtol=1e-10, atol=1e-15)
+    for k in ('n_coll', 'n_sfc', 'n_roulette_kill', 'photons'):
+        assert a['stats'][k] == b['stats'][k]
+
+
 def test_accumulate_flag(solver):
     sc = scenes.scene_3d(nx=8, ny=6)
     opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=1, wmin=0.2)
