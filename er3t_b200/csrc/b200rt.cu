@@ -268,6 +268,15 @@ enum { CNT_PHOT = 0, CNT_TENT = 1, CNT_COLL = 2, CNT_SFC = 3, CNT_LE = 4, CNT_VI
 #define ACC(k) sm.acc[(k) * blockDim.x + threadIdx.x]
 #define CNT(k) sm.cnt[(k) * blockDim.x + threadIdx.x]
 
+// One copy of the Philox rounds for the whole transport kernel: the six draw sites would otherwise inline ~70 instructions
+// each.  The hot loop (~38 KB of SASS) is larger than the instruction cache, and throughput reacts to its layout: measured
+// on config 2 with prebuilt variants (tools/gpu_variants.sh, profiles/README.md r01_m), this Philox + an out-of-line
+// abs_tau_at give 1478 M photons/s against 1430 M with both inlined; moving further cold code out of line lost again.
+__device__ __noinline__ float4 philox_u01x4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+    const uint4 r = philox4x32_10(c0, c1, c2, 0xB200u, k0, k1);
+    return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
 // A photon in registers (while a lane works on it).  Between phases it lives in its warp's shared-memory pool.
 struct Photon {
     float x, y, z;
@@ -438,15 +447,19 @@ __device__ __forceinline__ int find_layer(const Smem& sm, int l0, int l1, float 
     return lo;
 }
 
-// gas-absorption optical depth of a straight leg from (za, layer iza) to (zb, layer izb) of length `dist`
+// gas-absorption optical depth of a straight leg from (za, layer iza) to (zb, layer izb) of length `dist`.
+// Out of line and by value (three call sites; keeps the hot loop small).
+__device__ __noinline__ float abs_tau_at(const float* __restrict__ ab, const float* __restrict__ cb, float za, float zla, int iza,
+                                         float zb, float zlb, int izb, float dist, float inv_absdz) {
+    if (iza == izb) return __ldg(ab + iza) * dist;
+    const float ca = __ldg(cb + iza) + __ldg(ab + iza) * (za - zla);
+    const float c2 = __ldg(cb + izb) + __ldg(ab + izb) * (zb - zlb);
+    return fabsf(c2 - ca) * inv_absdz;
+}
 __device__ __forceinline__ float abs_tau(const DevScene& S, const Smem& sm, int job, float za, int iza, float zb, int izb,
                                          float dist, float inv_absdz) {
-    const float* ab = S.job_abs + size_t(job) * S.nz;
-    if (iza == izb) return __ldg(ab + iza) * dist;
-    const float* cb = S.job_cabs + size_t(job) * (S.nz + 1);
-    const float ca = __ldg(cb + iza) + __ldg(ab + iza) * (za - sm.z[iza]);
-    const float c2 = __ldg(cb + izb) + __ldg(ab + izb) * (zb - sm.z[izb]);
-    return fabsf(c2 - ca) * inv_absdz;
+    return abs_tau_at(S.job_abs + size_t(job) * S.nz, S.job_cabs + size_t(job) * (S.nz + 1), za, sm.z[iza], iza, zb, sm.z[izb], izb,
+                      dist, inv_absdz);
 }
 
 // Exact optical depth toward a sensor for oblique views and sensors inside the atmosphere.
@@ -782,12 +795,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
     int nD = NP, nF = 0, nE = 0, nC = 0, nS = 0;
     const int ND_DONE = -(1 << 29);
 
-#define RNG4(out)                                                                                              \
-    {                                                                                                          \
-        const unsigned long long seed_ = S.jobs[p.job].seed;                                                   \
-        const uint4 r_ = philox4x32_10(p.rc0, p.rc1, p.rc2, 0xB200u, unsigned(seed_), unsigned(seed_ >> 32));  \
-        p.rc2++;                                                                                               \
-        out = make_float4(u01(r_.x), u01(r_.y), u01(r_.z), u01(r_.w));                                          \
+#define RNG4(out)                                                                                     \
+    {                                                                                                 \
+        const unsigned long long seed_ = S.jobs[p.job].seed;                                          \
+        out = philox_u01x4(p.rc0, p.rc1, p.rc2, unsigned(seed_), unsigned(seed_ >> 32));              \
+        p.rc2++;                                                                                      \
     }
 // push the slots of the lanes for which `cond` holds onto queue `q` (length `cnt`); `val` is the queue entry
 #define QPUSH(q, cnt, cond, val)                                              \
@@ -1556,7 +1568,14 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     // coarse (emptiness) level: 2^shx x 2^shy fine cells horizontally, cmz fine slabs vertically
     auto log2floor = [](int v) { int s = 0; while ((2 << s) <= v) ++s; return s; };
     int shx = log2floor(std::max(1, opt->cmx > 0 ? opt->cmx : 4)), shy = log2floor(std::max(1, opt->cmy > 0 ? opt->cmy : 4));
-    int cmz = opt->cmz > 0 ? opt->cmz : 5;
+    // With vertical runs of empty cells (3-D layers of equal thickness) the finest z granularity is best: a run is crossed
+    // in one step however many groups it spans (tools/sweep_sv.py: cmz = 1 gives 19.7 cell steps per photon on config 2
+    // against 21.4 for cmz = 5).  Without runs a coarse cell is about as high as it is wide.
+    bool uniform3 = nz3 > 0;
+    for (int k = 0; k < nz3; ++k)
+        if (std::fabs((zg[iz0 + k + 1] - zg[iz0 + k]) - (zg[iz0 + 1] - zg[iz0])) > 1e-5 * (zg[iz0 + 1] - zg[iz0])) uniform3 = false;
+    const bool runs_ok = uniform3 && !per_level && opt->empty_runs >= 0;
+    int cmz = opt->cmz > 0 ? opt->cmz : (runs_ok ? 1 : 5);
     if (per_level) { shx = 0; shy = 0; cmz = 1; }
     S.flight_steps = opt->flight_steps > 0 ? opt->flight_steps : 16;
     S.event_min = opt->event_min > 0 ? opt->event_min : 12;
@@ -1631,10 +1650,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         for (int g = 0; g < S.ngroup; ++g) if (g_cz[g] == 0) gid3_0 = g;
         for (int g = 0; g < S.ngroup; ++g) if (g_cz[g] >= 0) S.maj1d_blk = std::max(S.maj1d_blk, g_maj1d[g]);
         const double dz0 = zg[iz0 + 1] - zg[iz0];
-        bool uniform = true;
-        for (int k = 0; k < nz3; ++k) if (std::fabs((zg[iz0 + k + 1] - zg[iz0 + k]) - dz0) > 1e-5 * dz0) uniform = false;
         for (int s = 0; s < S.nslab_z; ++s) if (czv[s] == 0) S.uz_s0 = s;
-        if (uniform && !per_level && opt->empty_runs >= 0) {
+        if (runs_ok) {
             S.uz_ok = 1;
             S.uz_z0 = float(zg[iz0]);
             S.uz_inv = float(1.0 / (dz0 * svz));
