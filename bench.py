@@ -111,11 +111,19 @@ def ncu_traffic():
     return None
 
 
+def host_cores():
+    """Host threads this process may use.  Passed to the oracle explicitly: torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_rate(kw, abs0, seconds=15.0, nthreads=0):
     """Bounded sample of the same workload on the host cores with the oracle port; returns (photons/s, photons, cores)."""
     import oracle
     from er3t_b200.rtm.mca import mcarats_ng
-    cores = nthreads if nthreads > 0 else (os.cpu_count() or 1)
+    cores = nthreads = nthreads if nthreads > 0 else host_cores()
     rate = None
     nphot = 40000
     total_t = 0.0
@@ -166,19 +174,19 @@ def main():
         import oracle
         from er3t_b200 import abi
         from er3t_b200.rtm.mca import mcarats_ng
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         # size the per-step sample from a probe so that the whole run ends within a few minutes
-        probe, _, _ = cpu_oracle_rate(kw, abs0, seconds=6.0)
+        probe, _, _ = cpu_oracle_rate(kw, abs0, seconds=6.0, nthreads=cores)
         nstep = max(1, args.steps + args.warmup)
         sample = int(max(2e4, min(args.photons, probe * 100.0 / nstep)))
         k = dict(kw); k.update(photons=sample, Nrun=1, dry_run=True)
         m = mcarats_ng(**k)
         jobs, keep = abi.make_jobs(**m.jobs_args)
         for _ in range(args.warmup):
-            oracle.run(m.scene, m.options, jobs)
+            oracle.run(m.scene, m.options, jobs, nthreads=cores)
         t0 = time.time()
         for _ in range(args.steps):
-            oracle.run(m.scene, m.options, jobs)
+            oracle.run(m.scene, m.options, jobs, nthreads=cores)
         dt = time.time() - t0
         val = sample * args.steps / dt
         line = {'impl': 'reference', 'metric': 'photons/s', 'value': val, 'unit': 'photons/s', 'n_gpus': args.gpus, 'steps': args.steps,
