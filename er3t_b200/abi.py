@@ -198,7 +198,7 @@ class HostScene:
             s.np3d, s.nz3 = self.ext3d.shape[3], self.ext3d.shape[2]
             s.iz3l = int(iz3l)
             s.ext3d, s.omg3d, s.apf3d = _ptr(self.ext3d), _ptr(self.omg3d), _ptr(self.apf3d)
-            if abs3d is not None and np.any(np.asarray(abs3d) != 0.0):
+            if abs3d is not None and np.asarray(abs3d).any():
                 b3 = np.asarray(abs3d)
                 if b3.ndim == 4:
                     b3 = b3[..., 0]

@@ -180,7 +180,7 @@ class mca_atm_3d:
         # that results match "MCARaTS as driven by er3t"; mcarats_ng(..., iz3l_fix=True) undoes it.
         self.nml['Atm_iz3l'] = {'data': iz3l + 1, 'unit': 'N/A', 'name': 'layer index of first 3D layer'}
         self.nml['Atm_tmpa3d'] = {'data': atm_tmp, 'units': 'K', 'name': 'Temperature deviation'}
-        self.nml['Atm_abst3d'] = {'data': atm_abs, 'units': '/m', 'name': 'Absorption coefficients deviation'}
+        self.nml['Atm_abst3d'] = {'data': atm_abs, 'units': '/m', 'name': 'Absorption coefficients deviation', 'all_zero': True}
         self.nml['Atm_extp3d'] = {'data': atm_ext, 'units': '/m', 'name': 'Extinction coefficients'}
         self.nml['Atm_omgp3d'] = {'data': atm_omg, 'units': 'N/A', 'name': 'Single scattering Albedo'}
         self.nml['Atm_apfp3d'] = {'data': atm_apf, 'units': 'N/A', 'name': 'Phase function'}

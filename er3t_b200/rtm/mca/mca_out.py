@@ -29,12 +29,15 @@ def cal_factors(date, abs_obj, Nz, Ng):
     weight = abs_obj.coef['weight']['data']
     slit = abs_obj.coef['slit_func']['data']
     solar = abs_obj.coef['solar']['data']
-    norm = np.zeros(Nz, dtype=np.float32)
-    factors = np.zeros((Nz, Ng), dtype=np.float32)
-    for iz in range(Nz):
-        norm[iz] = sol_fac / (weight * slit[zz[iz], :]).sum()
-        for ig in range(Ng):
-            factors[iz, ig] = norm[iz] * solar[ig] * weight[ig] * slit[zz[iz], ig]
+    # vectorised restatement of the reference's double loop (same operation order and float32 roundings: norm is rounded
+    # to float32 first, the products are formed in float64 and rounded once)
+    weight = np.asarray(weight); solar = np.asarray(solar); slit = np.asarray(slit)
+    rows = np.ascontiguousarray(weight[np.newaxis, :Ng] * slit[zz, :Ng]) if weight.size == Ng and slit.shape[1] == Ng else None
+    if rows is None:
+        norm = np.array([sol_fac / (weight * slit[zz[iz], :]).sum() for iz in range(Nz)], dtype=np.float32)
+    else:
+        norm = (sol_fac / rows.sum(axis=1)).astype(np.float32)
+    factors = (norm.astype(np.float64)[:, np.newaxis] * solar[np.newaxis, :Ng] * weight[np.newaxis, :Ng] * slit[zz, :Ng]).astype(np.float32)
     toa = np.sum(sol_fac * solar * weight)
     return factors, toa
 

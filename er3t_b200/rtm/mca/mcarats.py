@@ -329,7 +329,7 @@ class mcarats_ng:
                 iz3l -= 1
             kw.update(nx=int(a3['Atm_nx']['data']), ny=int(a3['Atm_ny']['data']), dx=float(a3['Atm_dx']['data']), dy=float(a3['Atm_dy']['data']),
                       iz3l=iz3l, ext3d=a3['Atm_extp3d']['data'], omg3d=a3['Atm_omgp3d']['data'], apf3d=a3['Atm_apfp3d']['data'],
-                      abs3d=a3['Atm_abst3d']['data'])
+                      abs3d=None if a3['Atm_abst3d'].get('all_zero') else a3['Atm_abst3d']['data'])
         if self.sca is not None and int(n0.get('Sca_npf', 0)) > 0:
             kw.update(ang=self.sca.pha.data['ang']['data'], pha=self.sca.pha.data['pha']['data'])
         if self.sfc_2d:
