@@ -1582,6 +1582,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     svx = std::min(svx, sc->nx); svy = std::min(svy, sc->ny); svz = std::max(1, std::min(svz, std::max(1, nz3)));
     S.svx = svx; S.svy = svy; S.svz = svz;
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
+    // the z-group tables live in shared memory: at most 128 groups in the 3-D block unless the caller chose cmz
+    if (opt->cmz <= 0 && !per_level && S.ncz > 128 * cmz) cmz = (S.ncz + 127) / 128;
     S.Sx = float(sc->dx * svx); S.Sy = float(sc->dy * svy); S.inv_Sx = 1.0f / S.Sx; S.inv_Sy = 1.0f / S.Sy;
     S.inv_Lx = 1.0f / S.Lx; S.inv_Ly = 1.0f / S.Ly;
     S.Lux = float(double(sc->nx) / svx); S.Luy = float(double(sc->ny) / svy);
