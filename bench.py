@@ -100,12 +100,12 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_traffic():
-    """per-launch DRAM bytes of the transport kernel from the committed ncu --set full capture (or None)."""
+def ncu_traffic(key='transport_kernel_dram_bytes_per_launch'):
+    """per-launch DRAM bytes of the transport kernel (or the headline counters) from the committed ncu captures, or None."""
     p = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.isfile(p):
         try:
-            return json.load(open(p)).get('transport_kernel_dram_bytes_per_launch')
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
@@ -294,7 +294,8 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': 'transport_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': ncu_traffic(), 'peak_source': peak_src, 'bytes_alg_per_launch': float(np.mean(bytes_alg)),
                 'kernel_ms_per_launch': float(np.mean(kern_ms)),
-                'bytes_alg_per_photon': float(np.mean(bytes_alg)) / (photons_step / world)}
+                'bytes_alg_per_photon': float(np.mean(bytes_alg)) / (photons_step / world),
+                'ncu': ncu_traffic('ncu_capture')}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r, n, cores = cpu_oracle_rate(kw, abs0, seconds=15.0)
