@@ -537,31 +537,41 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
     float tmz = fminf(T, (zl[lz] - za) * isz);
     const float* base = S.ext3tot;
     float t = 0.0f, tau3 = 0.0f;
+// one voxel: SEG = path length inside the current voxel, IDX = index of the next one, DONE = the current one is the last
+#define LE_STEP(SEG, IDX, DONE)                                               \
+    {                                                                         \
+        const float tn = fminf(fminf(tmx, tmy), tmz);                         \
+        SEG = tn - t;                                                         \
+        t = tn;                                                               \
+        ++n_visit;                                                            \
+        const bool cx = tmx <= tmy && tmx <= tmz;                             \
+        const bool cy = !cx && tmy <= tmz;                                    \
+        const bool cz = !(cx || cy);                                          \
+        int nfx = fx + sx, nfy = fy + sy;                                     \
+        nfx = nfx >= S.nx ? 0 : (nfx < 0 ? S.nx - 1 : nfx);                   \
+        nfy = nfy >= S.ny ? 0 : (nfy < 0 ? S.ny - 1 : nfy);                   \
+        fx = cx ? nfx : fx;                                                   \
+        fy = cy ? nfy : fy;                                                   \
+        lz = cz ? lz + dl : lz;                                               \
+        tmx = cx ? tmx + tdx : tmx;                                           \
+        tmy = cy ? tmy + tdy : tmy;                                           \
+        DONE = tn >= T || lz == lzend;                                        \
+        const int lzc = min(S.nz3 - 1, max(0, lz));                           \
+        tmz = cz ? fminf(T, (zl[lzc] - za) * isz) : tmz;                      \
+        IDX = (lzc * S.ny + fy) * S.nx + fx;                                  \
+    }
     float e = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
     for (;;) {
-        const float tn = fminf(fminf(tmx, tmy), tmz);
-        const float seg = tn - t;
-        t = tn;
-        ++n_visit;
-        const bool cx = tmx <= tmy && tmx <= tmz;
-        const bool cy = !cx && tmy <= tmz;
-        const bool cz = !(cx || cy);
-        int nfx = fx + sx, nfy = fy + sy;
-        nfx = nfx >= S.nx ? 0 : (nfx < 0 ? S.nx - 1 : nfx);
-        nfy = nfy >= S.ny ? 0 : (nfy < 0 ? S.ny - 1 : nfy);
-        fx = cx ? nfx : fx;
-        fy = cy ? nfy : fy;
-        lz = cz ? lz + dl : lz;
-        tmx = cx ? tmx + tdx : tmx;
-        tmy = cy ? tmy + tdy : tmy;
-        const bool done = tn >= T || lz == lzend;
-        const int lzc = min(S.nz3 - 1, max(0, lz));
-        tmz = cz ? fminf(T, (zl[lzc] - za) * isz) : tmz;
-        const float en = done ? 0.0f : __ldg(base + (lzc * S.ny + fy) * S.nx + fx);   // next voxel: in flight while this one is consumed
+        float seg;
+        int inext;
+        bool done;
+        LE_STEP(seg, inext, done);
+        const float en = done ? 0.0f : __ldg(base + inext);   // next voxel: in flight while this one is consumed
         tau3 = fmaf(e, seg, tau3);
         if (done) break;
         e = en;
     }
+#undef LE_STEP
     *n_visit_out = n_visit;
     return tau + tau3;
 }

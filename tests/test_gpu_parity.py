@@ -157,6 +157,48 @@ def test_3d_empty_runs_tall_block(solver, sv, cm, runs, uniform):
     assert mean_close(g['rad'], c['rad'], nslab)
 
 
+@pytest.mark.parametrize('nx,ny,nz3', [(1, 1, 3), (3, 5, 4), (7, 2, 1)])
+def test_3d_ragged_and_degenerate_grids(solver, nx, ny, nz3):
+    """Grids the automatic cell sizes do not divide (odd column counts, one column, one 3-D layer): flux and nadir
+    radiance against the oracle."""
+    sc = scenes.scene_3d(nx=nx, ny=ny, nz3=nz3, sensors=[dict(the=180.0, phi=270.0, nxr=nx, nyr=ny)], seed=5)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE | abi.TARGET_FLUX, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(100000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (ny, nx))
+    assert np.max(np.abs(z)) < 5.0
+    assert mean_close(g['rad'], c['rad'], nslab)
+    gf = g['flux'].reshape(nslab, 3, -1, ny, nx).mean(axis=(0, 3, 4))
+    cf = c['flux'].reshape(nslab, 3, -1, ny, nx).mean(axis=(0, 3, 4))
+    for var, lev in ((2, -1), (1, 0)):
+        assert abs(gf[var, lev] / cf[var, lev] - 1.0) < 2 * FLUX_RTOL, (var, lev, gf[var, lev], cf[var, lev])
+
+
+def test_empty_atmosphere_and_zero_photons(solver):
+    """No extinction at all over a black surface: every photon reaches the ground unscattered (direct = total down-flux =
+    mu0 at every level, no up-flux, T = 1); and a job list without photons runs and leaves the tallies at zero."""
+    z = scenes.std_z()
+    nz = z.size - 1
+    sc = abi.HostScene(z, np.zeros((1, nz)), np.ones((1, nz)), -np.ones((1, nz)), sfc_type=1, sfc_param=(0.0, 0, 0, 0, 0),
+                       src_the=180.0 - 60.0, src_phi=270.0, src_qmax=0.0, sensors=[dict(the=180.0, phi=270.0, nxr=1, nyr=1)])
+    opt = abi.make_options(target=abi.TARGET_RADIANCE | abi.TARGET_FLUX, nslab=1, wmin=0.2)
+    jobs, keep = abi.make_jobs([50000], [3], [0])
+    solver.upload_scene(sc, opt); solver.run(jobs)
+    r = solver.results()
+    st = r['stats']
+    assert st['n_coll'] == 0 and st['n_sfc'] == 50000
+    assert abs(st['w_sfc_abs'] / st['photons'] - 1.0) < 1e-12 and st['w_toa_up'] == 0.0
+    f = r['flux'].reshape(3, nz + 1)
+    assert np.allclose(f[0], 0.5, rtol=1e-6) and np.allclose(f[1], 0.5, rtol=1e-6) and np.all(f[2] == 0.0)
+    assert np.all(r['rad'] == 0.0)
+    jobs0, keep0 = abi.make_jobs([0, 0], [1, 2], [0, 0])
+    solver.run(jobs0)
+    r0 = solver.results()
+    assert r0['stats']['photons'] == 0 and np.all(r0['flux'] == 0.0) and np.all(r0['rad'] == 0.0)
+
+
 def test_3d_oblique_multi_sensor(solver):
     sens = [dict(the=180.0, phi=270.0, nxr=16, nyr=12),
             dict(the=180.0 - 35.0, phi=30.0, nxr=16, nyr=12),
