@@ -258,15 +258,25 @@ struct Smem {
     const int4* slabB;    // [nslab_z]   (first layer, one-past-last layer, coarse group, -)
     const float4* grpA;   // [ngroup]    (zlo, zhi, 1-D majorant, bits: first fine slab | one-past-last fine slab << 16)
     const int4* grpB;     // [ngroup]    (first fine slab, one-past-last fine slab, first layer, one-past-last layer)
-    double* acc;          // per-thread energy accumulators [4][blockDim]: toa, sfc, atm, roulette
+    double* acc;          // energy sums [4][32]: toa, sfc, (unused), roulette; one slot per lane and block
+    double* acc_atm;      // atmospheric absorption: one slot per thread
     double* ftal;         // block-private flux tally (same layout as the global one) or nullptr
     double* htal;         // block-private heating tally or nullptr
-    unsigned* cnt;        // per-thread event counters [8][blockDim]
+    unsigned* cnt;        // event counters [8][32]: one slot per lane and block (flushed to 64-bit totals per block)
 };
 enum { ACC_TOA = 0, ACC_SFC = 1, ACC_ATM = 2, ACC_RR = 3 };
 enum { CNT_PHOT = 0, CNT_TENT = 1, CNT_COLL = 2, CNT_SFC = 3, CNT_LE = 4, CNT_VISIT = 5, CNT_TALLY = 6, CNT_KILL = 7 };
-#define ACC(k) sm.acc[(k) * blockDim.x + threadIdx.x]
-#define CNT(k) sm.cnt[(k) * blockDim.x + threadIdx.x]
+// Energy sums and event counters: one slot per LANE and block (not per thread), updated with shared-memory atomics -- the
+// lanes of a warp hit 32 different addresses, warps of a block rarely collide.  2 KB per block instead of 20 KB: with
+// the photon pools this brings two blocks under the 196 KB shared-memory carve-out and leaves 60 KB of L1 to the voxel
+// and majorant gathers instead of 22 KB.
+// The atmospheric-absorption sum is touched at every collision and keeps a plain per-THREAD slot (load, add, store).
+#define ACC_ADD(k, v)                                                                        \
+    {                                                                                        \
+        if ((k) == ACC_ATM) sm.acc_atm[threadIdx.x] += (v);                                  \
+        else tally_add_shared(&sm.acc[(k) * 32 + (threadIdx.x & 31)], (v));                  \
+    }
+#define CNT_ADD(k, v) cnt_add_shared(&sm.cnt[(k) * 32 + (threadIdx.x & 31)], (v))
 
 // One copy of the Philox rounds for the whole transport kernel: the six draw sites would otherwise inline ~70 instructions
 // each.  The hot loop (~38 KB of SASS) is larger than the instruction cache, and throughput reacts to its layout: measured
@@ -397,6 +407,10 @@ __device__ __forceinline__ float wrapf(float x, float L, float invL) {
 }
 
 __device__ __forceinline__ void tally_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void cnt_add_shared(unsigned* p, unsigned v) {
+    const unsigned a = unsigned(__cvta_generic_to_shared(p));
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tally_add_shared(double* p, double v) {
     const unsigned a = unsigned(__cvta_generic_to_shared(p));
     asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
@@ -427,14 +441,14 @@ __device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, co
     tally_at(sm.ftal ? sm.ftal : S.flux, sm.ftal != nullptr, S.job_fscale + p.job * (S.nz + 1) + lev, &S.jobs[p.job].flux_off,
              (unsigned long long)(var * (S.nz + 1) + lev) * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx),
              double(p.w));
-    if (!sm.ftal) CNT(CNT_TALLY)++;          // counts updates that reach global memory; block-private ones are counted at the flush
+    if (!sm.ftal) CNT_ADD(CNT_TALLY, 1u);          // counts updates that reach global memory; block-private ones are counted at the flush
 }
 __device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
     int fx, fy;
     tally_col(S, p, fx, fy);
     tally_at(sm.htal ? sm.htal : S.heat, sm.htal != nullptr, S.job_fscale + p.job * (S.nz + 1) + iz, &S.jobs[p.job].heat_off,
              (unsigned long long)iz * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx), dep);
-    if (!sm.htal) CNT(CNT_TALLY)++;
+    if (!sm.htal) CNT_ADD(CNT_TALLY, 1u);
 }
 
 // layer that contains z among layers [l0, l1)
@@ -601,7 +615,7 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
             } else {
                 t1 += __ldg(S.tu3 + (iz - S.iz0 + 1) * nxy + fy * S.nx + fx) + s3 * (sm.z[iz + 1] - p.z);
             }
-            CNT(CNT_VISIT)++;
+            CNT_ADD(CNT_VISIT, 1u);
         }
         return fmaxf(0.0f, t1) * se.inv_sz;
     }
@@ -609,7 +623,7 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
     unsigned nv = 0;
     const RayTarget rt = {se.s, se.zt, se.lt};
     const float t = le_tau_generic(S, sm.z, sm.e1tot, sm.e1cum, rt, p.x, p.y, p.z, iz, p.job, p.flags & FL_ABS, frozen ? 1 : 0, fx, fy, in3, &nv);
-    CNT(CNT_VISIT) += nv;
+    CNT_ADD(CNT_VISIT, nv);
     return t;
 }
 
@@ -630,8 +644,8 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
     }
     const DevJob& J = S.jobs[p.job];
     tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
-    CNT(CNT_LE)++;
-    CNT(CNT_TALLY)++;
+    CNT_ADD(CNT_LE, 1u);
+    CNT_ADD(CNT_TALLY, 1u);
 }
 
 // All-sky camera (Rad_mrkind = 1): contribution of one event, per unit photon weight, to the radiance the camera at
@@ -746,10 +760,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         float4* grpA = q4; q4 += S.ngroup;
         int4* grpB = reinterpret_cast<int4*>(q4); q4 += S.ngroup;
         double* acc = reinterpret_cast<double*>(q4);
-        double* tal = acc + 4 * blockDim.x;
+        double* acc_atm = acc + 4 * 32;
+        double* tal = acc_atm + blockDim.x;
         const int ntal = PL ? S.ntal_flux_smem + S.ntal_heat_smem : 0;
         unsigned* cnt = reinterpret_cast<unsigned*>(tal + ntal);
-        float* q = reinterpret_cast<float*>(cnt + 8 * blockDim.x);
+        float* q = reinterpret_cast<float*>(cnt + 8 * 32);
         float* z = q; q += S.nz + 1;
         float* e1tot = q; q += S.nz;
         float* e1cum = q; q += S.nz + 1;
@@ -779,14 +794,17 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             grpA[i] = make_float4(S.zgrd[l0], S.zgrd[l1], S.group_maj1d[i], __int_as_float(int(unsigned(s0) | (unsigned(s1) << 16))));
             grpB[i] = make_int4(s0, s1, l0, l1);
         }
-        for (int k = 0; k < 4; ++k) acc[k * blockDim.x + threadIdx.x] = 0.0;
+        if (threadIdx.x < 32) {
+            for (int k = 0; k < 4; ++k) acc[k * 32 + threadIdx.x] = 0.0;
+            for (int k = 0; k < 8; ++k) cnt[k * 32 + threadIdx.x] = 0u;
+        }
+        acc_atm[threadIdx.x] = 0.0;
         for (int i = threadIdx.x; i < ntal; i += blockDim.x) tal[i] = 0.0;
         sm.ftal = (PL && S.ntal_flux_smem > 0) ? tal : nullptr;
         sm.htal = (PL && S.ntal_heat_smem > 0) ? tal + S.ntal_flux_smem : nullptr;
-        for (int k = 0; k < 8; ++k) cnt[k * blockDim.x + threadIdx.x] = 0u;
         for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
-        sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.cnt = cnt;
+        sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.acc_atm = acc_atm; sm.cnt = cnt;
     }
     __syncthreads();
 
@@ -876,7 +894,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     p.x = (float(p.cix) + 0.5f) * S.dx; p.y = (float(p.ciy) + 0.5f) * S.dy;
                 }
                 p.tau = -__logf(v.x);
-                CNT(CNT_PHOT)++;
+                CNT_ADD(CNT_PHOT, 1u);
                 if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
                 pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
@@ -966,7 +984,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     if (PL && (p.flags & FL_ABS)) {
                         // flux / heating targets: weight must be current at every level (slabs are single layers here)
                         const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
-                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
                             heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
@@ -1050,10 +1068,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 if (!PL && (p.flags & FL_ABS)) {
                     const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
                     const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, S.nz - 1, p.leg, inv_absdz));
-                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                     p.w = wn;
                 }
-                ACC(ACC_TOA) += double(p.w);
+                ACC_ADD(ACC_TOA, double(p.w));
             } else if (ev == EV_TENT) {
                 const bool frozen = FZ && (p.flags & FL_FROZEN);
                 const bool ev_empty = (p.flags & FL_EMPTY) != 0;
@@ -1083,7 +1101,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
                     }
                     vox = ((izn - S.iz0) * S.ny + fy) * S.nx + fx;
-                    if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT(CNT_TENT)++; }
+                    if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT_ADD(CNT_TENT, 1u); }
                 }
                 p.tau = -__logf(u.y);
                 float uc = u.x * p.M;
@@ -1093,7 +1111,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     if (!PL && (p.flags & FL_ABS)) {
                         const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
                         const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, izn, p.leg, inv_absdz));
-                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         p.w = wn;
                     }
                     float omg = 1.0f, apf = 0.0f;
@@ -1122,10 +1140,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                             uc -= e;
                         }
                     }
-                    CNT(CNT_COLL)++;
+                    CNT_ADD(CNT_COLL, 1u);
                     const float wn = p.w * omg;
                     if (wn < p.w) {
-                        ACC(ACC_ATM) += double(p.w) - double(wn);
+                        ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
                     }
                     p.w = wn;
@@ -1189,10 +1207,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 if (!PL && (p.flags & FL_ABS)) {
                     const float inv_absdz = p.d.z != 0.0f ? fabsf(1.0f / p.d.z) : RT_INF;
                     const float wn = p.w * __expf(-abs_tau(S, sm, p.job, p.za, p.iza, p.z, 0, p.leg, inv_absdz));
-                    ACC(ACC_ATM) += double(p.w) - double(wn);
+                    ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                     p.w = wn;
                 }
-                CNT(CNT_SFC)++;
+                CNT_ADD(CNT_SFC, 1u);
                 RNG4(u);
                 const bool frozen = FZ && (p.flags & FL_FROZEN);
                 int sx, sy;
@@ -1225,12 +1243,12 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         const bool in3 = (S.nz3 > 0) && p.iz >= S.iz0 && p.iz < S.iz0 + S.nz3;
                         const float c = camera_le(S, sm.z, sm.e1tot, sm.e1cum, se, p.x, p.y, p.z, p.iz, p.job, p.flags & FL_ABS, fx, fy, in3, p.d, evk, apf,
                                                   sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], &pix, &nv);
-                        CNT(CNT_VISIT) += nv;
+                        CNT_ADD(CNT_VISIT, nv);
                         if (c > 0.0f) {
                             const DevJob& J = S.jobs[p.job];
                             tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
-                            CNT(CNT_LE)++;
-                            CNT(CNT_TALLY)++;
+                            CNT_ADD(CNT_LE, 1u);
+                            CNT_ADD(CNT_TALLY, 1u);
                         }
                         continue;
                     }
@@ -1253,12 +1271,12 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 if (apf >= 1.0f) { float4 v; RNG4(v); xi_tab = v.x; }
                 const float mu = phase_sample(S.pt, apf, u.z, xi_tab);
                 newd = rotate_dir(p.d, mu, RT_2PI * u.w);
-                if (p.order >= S.iso_max) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
+                if (p.order >= S.iso_max) { ACC_ADD(ACC_RR, -(double(p.w))); alive = false; break; }
             } else {
                 float3 wo;
                 const float fac = surface_sample(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, u, &wo);
                 const float wn = p.w * fac;
-                ACC(ACC_SFC) += double(p.w) - double(wn);
+                ACC_ADD(ACC_SFC, double(p.w) - double(wn));
                 p.w = wn;
                 if (!(p.w > 0.0f)) { alive = false; break; }
                 const float nrm = rsqrtf(wo.x * wo.x + wo.y * wo.y + wo.z * wo.z);
@@ -1282,10 +1300,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             if (p.w < S.wmin) {
                 float xi = u.w;
                 if (evk == EV_COLL) { float4 v; RNG4(v); xi = v.x; }
-                if (xi * S.wfac < p.w) { ACC(ACC_RR) += double(S.wfac) - double(p.w); p.w = S.wfac; }
-                else { ACC(ACC_RR) -= double(p.w); CNT(CNT_KILL)++; alive = false; break; }
+                if (xi * S.wfac < p.w) { ACC_ADD(ACC_RR, double(S.wfac) - double(p.w)); p.w = S.wfac; }
+                else { ACC_ADD(ACC_RR, -(double(p.w))); CNT_ADD(CNT_KILL, 1u); alive = false; break; }
             }
-            if (p.w < 1e-30f) { ACC(ACC_RR) -= double(p.w); alive = false; break; }
+            if (p.w < 1e-30f) { ACC_ADD(ACC_RR, -(double(p.w))); alive = false; break; }
         } while (0);
 
         if (have && alive) pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
@@ -1301,39 +1319,49 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         __syncthreads();
         for (int i = threadIdx.x; i < S.ntal_flux_smem; i += blockDim.x) {
             const double v = sm.ftal[i];
-            if (v != 0.0) { tally_add(S.flux + i, v); CNT(CNT_TALLY)++; }
+            if (v != 0.0) { tally_add(S.flux + i, v); CNT_ADD(CNT_TALLY, 1u); }
         }
         for (int i = threadIdx.x; i < S.ntal_heat_smem; i += blockDim.x) {
             const double v = sm.htal[i];
-            if (v != 0.0) { tally_add(S.heat + i, v); CNT(CNT_TALLY)++; }
+            if (v != 0.0) { tally_add(S.heat + i, v); CNT_ADD(CNT_TALLY, 1u); }
         }
     }
-    // ---- flush the per-thread event counters (warp reduce, then one atomic per warp)
-    unsigned long long c[9] = {CNT(CNT_PHOT), n_cell, CNT(CNT_TENT), CNT(CNT_COLL), CNT(CNT_SFC), CNT(CNT_LE), CNT(CNT_VISIT),
-                               CNT(CNT_TALLY), CNT(CNT_KILL)};
-    double dsum[4] = {ACC(ACC_TOA), ACC(ACC_SFC), ACC(ACC_ATM), ACC(ACC_RR)};
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        unsigned long long v = c[i];
+    // ---- flush the event counters and energy sums: the cell counter lives in a register (one atomic per warp), the rest
+    //      in the block's per-lane slots (reduced by the first warp once every warp of the block has finished)
+    {
+        unsigned long long v = n_cell;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-        c[i] = v;
+        if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(S.stats) + 1, v);
+        double a = sm.acc_atm[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(FULL, a, o);
+        if (lane == 0) atomicAdd(&S.stats->w_atm, a);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double v = dsum[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-        dsum[i] = v;
-    }
-    if (lane == 0) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // DevStats order: photons, n_cell, n_tent, n_coll, n_sfc, n_le, n_le_visit, n_tally, n_kill
+        const int slot_of[8] = {0, 2, 3, 4, 5, 6, 7, 8};     // CNT_PHOT, CNT_TENT, CNT_COLL, CNT_SFC, CNT_LE, CNT_VISIT, CNT_TALLY, CNT_KILL
         unsigned long long* sc = reinterpret_cast<unsigned long long*>(S.stats);
-        for (int i = 0; i < 9; ++i) if (c[i]) atomicAdd(sc + i, c[i]);
-        atomicAdd(&S.stats->w_toa, dsum[0]); atomicAdd(&S.stats->w_sfc, dsum[1]);
-        atomicAdd(&S.stats->w_atm, dsum[2]); atomicAdd(&S.stats->w_rr, dsum[3]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            unsigned long long v = sm.cnt[i * 32 + lane];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+            if (lane == 0 && v) atomicAdd(sc + slot_of[i], v);
+        }
+        double dsum[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double v = sm.acc[i * 32 + lane];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+            dsum[i] = v;
+        }
+        if (lane == 0) {
+            atomicAdd(&S.stats->w_toa, dsum[0]); atomicAdd(&S.stats->w_sfc, dsum[1]);
+            atomicAdd(&S.stats->w_rr, dsum[3]);
+        }
     }
 }
-#undef ACC
-#undef CNT
+#undef ACC_ADD
+#undef CNT_ADD
 
 typedef void (*transport_fn)(const DevScene);
 template <int NP>
@@ -1348,6 +1376,7 @@ static transport_fn pick_transport(bool pl, bool fz, bool cam, int np) {
     switch (np) {
         case 32: return pick_transport_np<32>(pl, fz, cam);
         case 64: return pick_transport_np<64>(pl, fz, cam);
+        case 80: return pick_transport_np<80>(pl, fz, cam);
         case 128: return pick_transport_np<128>(pl, fz, cam);
         default: return pick_transport_np<96>(pl, fz, cam);
     }
@@ -1682,7 +1711,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.e1 = (const float*)H->e1.p; S.o1 = (const float*)H->o1.p; S.a1 = (const float*)H->a1.p;
     S.slab_lay0 = (const int*)H->slab_lay0.p; S.slab_cz = (const int*)H->slab_cz.p; S.slab_maj1d = (const float*)H->slab_maj1d.p;
     H->smem_tables = 16 * (2 * size_t(S.nslab_z) + 2 * size_t(S.ngroup)) + sizeof(float) * (size_t(nz + 1) * 2 + nz + size_t(3) * sc->np1d * nz);
-    H->smem_bytes = H->smem_tables + 256 * (4 * 8 + 8 * 4);
+    H->smem_bytes = H->smem_tables + 32 * (4 * 8 + 8 * 4) + 320 * 8;
     if (H->smem_bytes > 120 * 1024) return fail(H, B200RT_ERR_ARG, "1-D tables exceed shared memory (nz * np1d too large)");
     if (S.ncx > 65535 || S.ncy > 65535 || nz > 65535 || S.ncz > 65535 || S.ngroup > 32767)
         return fail(H, B200RT_ERR_ARG, "grid too large for the packed photon record (65535 cells per axis)");
@@ -1867,8 +1896,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     H->k_cam = false;
     for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
     H->pool_slots = opt->pool_slots;
-    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 96 && H->pool_slots != 128)
-        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 32, 64, 96 or 128");
+    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 80 && H->pool_slots != 96 && H->pool_slots != 128)
+        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 32, 64, 80, 96 or 128");
     H->opt = *opt;
     H->have_scene = true;
     H->ran = false;
@@ -1943,7 +1972,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     const int np = H->pool_slots > 0 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
-    const size_t smem = H->smem_tables + size_t(tpb) * (4 * 8 + 8 * 4) + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
+    const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
