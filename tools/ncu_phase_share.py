@@ -16,7 +16,7 @@ MARKS = [('pool_load/store', 'void pool_load'), ('wrapf', 'float wrapf'), ('tall
          ('queue pick', 'pick the fullest queue'), ('regeneration', '= regeneration'), ('flight', '= flight: geometry only'),
          ('tentative phase', '= tentative collisions (and escapes)'), ('event: load', '= event phase: collisions'),
          ('event: collision/surface', '---- hand-over record of the tentative phase'), ('event: local estimate', '---- local estimates toward every sensor'),
-         ('event: new direction+roulette', '---- new direction'), ('flush', '---- flush the per-thread event counters'),
+         ('event: new direction+roulette', '---- new direction'), ('flush', '---- flush the block-private tallies'),
          ('(end)', 'typedef void (*transport_fn)')]
 starts = []
 for name, pat in MARKS:
