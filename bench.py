@@ -310,4 +310,17 @@ def main():
 
 
 if __name__ == '__main__':
+    # stdout carries exactly ONE line (the JSON of rank 0): whatever libraries print while the benchmark runs (NCCL's
+    # version banner goes to stdout) is sent to stderr instead
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+
+    def print(*a, **k):                                    # noqa: A001  (only the JSON line is printed in this file)
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        _real_print(*a, **k)
+        sys.stdout.flush()
+        os.dup2(2, 1)
     main()
