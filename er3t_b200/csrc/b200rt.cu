@@ -24,8 +24,9 @@
 // Launch shape of the transport kernel.  Warps are independent (per-warp photon pools, no block-level synchronisation
 // after the table staging), so the block size only sets the granularity.  A B200 SM sub-partition holds 16 K registers:
 // 5 warps per scheduler need <= 96 registers per thread (tools/sweep_pool.py: 20 warps/SM at 96 registers beat 16 warps
-// at 123 registers by 4.5 % although ptxas then spills 48 bytes per thread).  Two blocks of 10 warps keep the per-block
-// tables (and the 1 KB the driver reserves per block) from eating the shared memory the photon pools need.
+// at 123 registers by 4.5 % although ptxas then spills a few words per thread; 22 or 24 warps at 80 registers lose 30 %,
+// profiles/README.md).  Shared memory per block: 82.6 KB of pools + tables + accumulators = 92.8 KB on config 2, so two
+// blocks stay under the 200 KB carve-out and ~56 KB of L1 remain for the voxel / majorant gathers.
 #ifndef RT_TPB
 #define RT_TPB 320
 #endif
@@ -731,16 +732,20 @@ __device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, f
 
 // Persistent-thread photon transport with queue-based path regeneration.
 //
-// Every WARP owns a pool of NP photon slots in shared memory (NP = 2..4 x the warp width) and every slot is in one of
-// three queues: DEAD (waiting for regeneration), FLY (waiting for the flight phase) or EVENT (parked at a tentative
-// collision, the surface or TOA).  The warp repeatedly picks the FULLEST queue, loads up to 32 photons of it into
-// registers -- one per lane --, runs that phase convergently and writes the photons back with their new state:
-//   regeneration   next global photon indices from one 64-bit atomic counter (one atomicAdd per warp and phase),
+// Every WARP owns a pool of NP photon slots in shared memory (NP = 3 x the warp width by default) and every slot is in
+// one of five LIFO queues: DEAD (waiting for regeneration), FLY (waiting for the flight phase), TENTATIVE (parked at a
+// tentative collision or at TOA), COLLISION (accepted, waiting for the scattering event) and SURFACE.  The warp
+// repeatedly picks the FULLEST queue, loads up to 32 photons of it into registers -- one per lane --, runs that ONE
+// phase convergently and writes the photons back with their new state:
+//   regeneration   next global photon indices from one 64-bit atomic counter (one atomicAdd per batch of 32),
 //                  Philox streams keyed by (job seed, global photon index): reproducible on any GPU count,
-//   flight         pure geometry on the two-level majorant grid (no RNG, no 3-D field look-ups); lanes that reach a
-//                  tentative collision / the surface / TOA park; ends when `event_min` lanes are parked,
-//   event          Philox draw + voxel extinction look-up + null-collision rejection for tentative collisions, then the
-//                  code shared by real collisions and surface hits: local estimates, new direction, roulette.
+//   flight         pure geometry on the two-level majorant grid with vertical runs of empty cells (no RNG, no 3-D field
+//                  look-ups); lanes that reach a tentative collision / the surface / TOA park; ends when `event_min`
+//                  lanes are parked,
+//   tentative      Philox draw + layer search + voxel extinction look-up + null-collision rejection; accepted
+//                  collisions read (omega, apf), apply implicit capture and hand over through the pool,
+//   collision /    local estimates toward every sensor, new direction (phase function / surface BRDF), roulette;
+//   surface        the two kinds come from separate queues, so a warp works on one kind at a time.
 // With NP >= 96 some queue always holds a full warp of work, so the phases run at (close to) 32 active lanes instead of
 // the ~11 a one-photon-per-lane loop reaches (profiles/README.md).  Nothing in the pool is shared between warps: the
 // only synchronisation is __syncwarp.
