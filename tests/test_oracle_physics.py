@@ -100,6 +100,26 @@ def test_single_scattering_radiance_analytic():
     assert abs(r['rad'][0] / expect - 1.0) < 0.01
 
 
+def test_reciprocity_of_multiple_scattering_at_oblique_angles():
+    """Helmholtz reciprocity of a plane-parallel atmosphere over a Lambertian surface: with the results normalised per
+    unit flux NORMAL to the beam, I(sun a -> view b) / mu_a = I(sun b -> view a) / mu_b at the same relative azimuth.
+    Pins the oblique local estimate under multiple scattering (Rayleigh + HG cloud of optical depth 2 + surface)."""
+    za, zb, dphi = 30.0, 55.0, 40.0
+    out = []
+    for sza, vza in ((za, zb), (zb, za)):
+        sc, _ = scenes.plane_parallel(sza=sza, cot=2.0, g=0.7, omega=0.98, albedo=0.2, with_sensor=False, qmax=0.0)
+        # sun travels toward azimuth 270 (src_phi); the sensor direction of travel (toward the sensor) is rotated by dphi
+        sc2 = abi.HostScene(sc.zgrd, sc.ext1d, sc.omg1d, sc.apf1d, sfc_type=1, sfc_param=(0.2, 0, 0, 0, 0), src_the=180.0 - sza, src_phi=270.0,
+                            src_qmax=0.0, sensors=[dict(the=180.0 - vza, phi=270.0 + dphi, nxr=1, nyr=1)])
+        opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=4, wmin=0.0)
+        jobs, keep = scenes.multi_seed_jobs(100000, 4, seed0=77)
+        r = oracle.run(sc2, opt, jobs)
+        m, se = scenes.mean_sem(r['rad'].reshape(4))
+        out.append((m / np.cos(np.deg2rad(sza)), se / np.cos(np.deg2rad(sza))))
+    (a, sa), (b, sb) = out
+    assert abs(a - b) < 4.0 * np.hypot(sa, sb) + 0.005 * a, (a, b, sa, sb)
+
+
 def test_ipa_equals_1d_on_uniform_field_and_3d_agrees():
     z = scenes.std_z(10, 10000.0)
     nz = 10
