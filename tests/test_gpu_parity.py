@@ -90,6 +90,28 @@ def test_plane_parallel_flux_and_radiance(solver, absorb):
     assert close(grm[0], crm[0], zr[0]), (grm[0], crm[0], zr[0])
 
 
+def test_plane_parallel_oblique_view_and_reciprocity(solver):
+    """Oblique parallel-projection sensor over a plane-parallel atmosphere (no 3-D block: the local-estimate optical depth is
+    the closed-form difference of cumulative profiles): against the oracle, and Helmholtz reciprocity
+    I(sun a -> view b) / mu_a = I(sun b -> view a) / mu_b on the GPU alone."""
+    za, zb, dphi = 30.0, 55.0, 40.0
+    nslab = 8
+    out = []
+    for sza, vza in ((za, zb), (zb, za)):
+        sc0, absg = scenes.plane_parallel(sza=sza, cot=2.0, g=0.7, omega=0.98, albedo=0.2, absorb=True, with_sensor=False, qmax=0.0)
+        sc = abi.HostScene(sc0.zgrd, sc0.ext1d, sc0.omg1d, sc0.apf1d, sfc_type=1, sfc_param=(0.2, 0, 0, 0, 0), src_the=180.0 - sza,
+                           src_phi=270.0, src_qmax=0.0, sensors=[dict(the=180.0 - vza, phi=270.0 + dphi, nxr=1, nyr=1)])
+        opt = abi.make_options(target=abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+        jobs, keep = scenes.multi_seed_jobs(200000, nslab, abs1d=absg)
+        g, c = run_both(solver, sc, opt, jobs)
+        check_energy(g['stats'])
+        assert mean_close(g['rad'], c['rad'], nslab)
+        m, se = scenes.mean_sem(g['rad'].reshape(nslab))
+        out.append((m / np.cos(np.deg2rad(sza)), se / np.cos(np.deg2rad(sza))))
+    (a, sa), (b, sb) = out
+    assert abs(a - b) < 4.0 * np.hypot(sa, sb) + 0.005 * a, (a, b, sa, sb)
+
+
 def test_plane_parallel_roulette_unbiased(solver):
     sc, absg = scenes.plane_parallel(omega=0.9, albedo=0.5)
     nslab = 8
