@@ -1,3 +1,4 @@
+"""High-statistics GPU-vs-oracle comparison of the local-estimate radiance (diagnostic; run on a GPU box: python tools/diag_le.py)."""
 import sys, os, time
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
