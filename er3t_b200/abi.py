@@ -48,7 +48,9 @@ class SceneStruct(C.Structure):
                 ('sfc_type', C.c_void_p), ('sfc_param', C.c_void_p),
                 ('src_the', C.c_double), ('src_phi', C.c_double), ('src_qmax', C.c_double), ('src_flx', C.c_double),
                 ('nrad', C.c_int32), ('_pad1', C.c_int32),
-                ('sensors', C.POINTER(Sensor))]
+                ('sensors', C.POINTER(Sensor)),
+                ('cer3d', C.c_void_p), ('nref', C.c_int32), ('_pad2', C.c_int32),
+                ('ref_tab', C.c_void_p), ('ssa_tab', C.c_void_p), ('asy_tab', C.c_void_p)]
 
 
 class Job(C.Structure):
@@ -64,6 +66,7 @@ class Options(C.Structure):
                 ('event_min', C.c_int32), ('empty_runs', C.c_int32), ('pool_slots', C.c_int32),
                 ('iso_ss', C.c_int32), ('iso_max', C.c_int32),
                 ('threads_per_block', C.c_int32), ('blocks_per_sm', C.c_int32), ('smem_tally', C.c_int32),
+                ('kernel', C.c_int32), ('_reserved', C.c_int32),
                 ('wmin', C.c_double), ('wfac', C.c_double)]
 
 
@@ -157,6 +160,7 @@ class HostScene:
 
     def __init__(self, zgrd, ext1d, omg1d, apf1d, nx=1, ny=1, dx=1.0e4, dy=1.0e4,
                  iz3l=1, ext3d=None, omg3d=None, apf3d=None, abs3d=None,
+                 cer3d=None, cer_tables=None,
                  ang=None, pha=None,
                  sfc_type=1, sfc_param=(0.0, 0.0, 0.0, 0.0, 0.0),
                  src_the=150.0, src_phi=270.0, src_qmax=0.533133, src_flx=1.0,
@@ -177,27 +181,42 @@ class HostScene:
         s.zgrd = _ptr(self.zgrd)
         s.ext1d, s.omg1d, s.apf1d = _ptr(self.ext1d), _ptr(self.omg1d), _ptr(self.apf1d)
 
+        self.cer3d = self.ref_tab = self.ssa_tab = self.asy_tab = None
         if ext3d is not None:
             e3 = np.asarray(ext3d)
             if e3.ndim == 3:
                 e3 = e3[..., np.newaxis]
-            o3 = np.asarray(omg3d)
-            a3 = np.asarray(apf3d)
-            if o3.ndim == 3:
-                o3 = o3[..., np.newaxis]
-            if a3.ndim == 3:
-                a3 = a3[..., np.newaxis]
-            if e3.shape[0] != nx or e3.shape[1] != ny or o3.shape != e3.shape or a3.shape != e3.shape:
+            if cer3d is not None:
+                # (omega, apf) are derived on the GPU from the effective radius (scene.cer3d, include/b200rt.h)
+                c3 = np.asarray(cer3d)
+                if c3.ndim == 3:
+                    c3 = c3[..., np.newaxis]
+                if c3.shape != e3.shape or e3.shape[3] != 1 or cer_tables is None:
+                    raise ValueError('Error [HostScene]: <cer3d> needs one 3-D component of the shape of <ext3d> and <cer_tables>.')
+                self.cer3d = _arr(c3, np.float32)
+                self.ref_tab, self.ssa_tab, self.asy_tab = [_arr(t, np.float64) for t in cer_tables]
+                o3 = a3 = None
+            else:
+                o3 = np.asarray(omg3d)
+                a3 = np.asarray(apf3d)
+                if o3.ndim == 3:
+                    o3 = o3[..., np.newaxis]
+                if a3.ndim == 3:
+                    a3 = a3[..., np.newaxis]
+            if e3.shape[0] != nx or e3.shape[1] != ny or (o3 is not None and (o3.shape != e3.shape or a3.shape != e3.shape)):
                 raise ValueError('Error [HostScene]: 3-D fields must have shape (nx, ny, nz3[, np3d]).')
             # zero-copy when the arrays are already float32 and C-contiguous (what mca_atm_3d produces): the library
             # transposes (nx, ny, nz3, np3d) -> [np3d][nz3][ny][nx] on the GPU (layout3d = 1)
             self.ext3d = _arr(e3, np.float32)
-            self.omg3d = _arr(o3, np.float32)
-            self.apf3d = _arr(a3, np.float32)
+            self.omg3d = None if o3 is None else _arr(o3, np.float32)
+            self.apf3d = None if a3 is None else _arr(a3, np.float32)
             s.layout3d = 1
             s.np3d, s.nz3 = self.ext3d.shape[3], self.ext3d.shape[2]
             s.iz3l = int(iz3l)
             s.ext3d, s.omg3d, s.apf3d = _ptr(self.ext3d), _ptr(self.omg3d), _ptr(self.apf3d)
+            if self.cer3d is not None:
+                s.cer3d, s.nref = _ptr(self.cer3d), int(self.ref_tab.size)
+                s.ref_tab, s.ssa_tab, s.asy_tab = _ptr(self.ref_tab), _ptr(self.ssa_tab), _ptr(self.asy_tab)
             if abs3d is not None and np.asarray(abs3d).any():
                 b3 = np.asarray(abs3d)
                 if b3.ndim == 4:
@@ -261,7 +280,7 @@ class HostScene:
     def nbytes(self):
         """bytes of scene arrays that cross the host -> device boundary in b200rt_upload_scene"""
         n = 0
-        for name in ('zgrd', 'ext1d', 'omg1d', 'apf1d', 'ext3d', 'omg3d', 'apf3d', 'abs3d', 'ang', 'pha', 'sfc_type', 'sfc_param'):
+        for name in ('zgrd', 'ext1d', 'omg1d', 'apf1d', 'ext3d', 'omg3d', 'apf3d', 'abs3d', 'cer3d', 'ang', 'pha', 'sfc_type', 'sfc_param'):
             arr = getattr(self, name, None)
             if arr is not None:
                 n += arr.nbytes
@@ -300,7 +319,7 @@ def make_jobs(nphot, seeds, slabs, abs1d=None, flx_scale=None, rad_scale=None):
 
 def make_options(solver=SOLVER_3D, target=TARGET_FLUX, nslab=1, shard_rank=0, shard_world=1,
                  sv=(0, 0, 0), iso_ss=1, iso_max=0, wmin=0.2, wfac=1.0, threads_per_block=0, blocks_per_sm=0,
-                 cm=(0, 0, 0), flight_steps=0, event_min=0, empty_runs=0, pool_slots=0, smem_tally=0):
+                 cm=(0, 0, 0), flight_steps=0, event_min=0, empty_runs=0, pool_slots=0, smem_tally=0, kernel=0):
     o = Options()
     o.solver, o.target, o.nslab = int(solver), int(target), int(nslab)
     o.shard_rank, o.shard_world = int(shard_rank), int(shard_world)
@@ -309,6 +328,7 @@ def make_options(solver=SOLVER_3D, target=TARGET_FLUX, nslab=1, shard_rank=0, sh
     o.flight_steps = int(flight_steps)
     o.event_min, o.empty_runs = int(event_min), int(empty_runs)
     o.pool_slots = int(pool_slots)
+    o.kernel = int(kernel)
     o.smem_tally = int(smem_tally)
     o.iso_ss, o.iso_max = int(iso_ss), int(iso_max)
     o.threads_per_block, o.blocks_per_sm = int(threads_per_block), int(blocks_per_sm)

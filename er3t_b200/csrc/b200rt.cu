@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +74,7 @@ struct DevJob {
 struct DevStats {
     unsigned long long photons, n_cell, n_tent, n_coll, n_sfc, n_le, n_le_visit, n_tally, n_kill;
     double w_toa, w_sfc, w_atm, w_rr;
+    unsigned long long hang;     // set by the watchdog of the role-specialised kernel (a warp idled for seconds)
 };
 
 struct DevScene {
@@ -145,10 +147,37 @@ struct DevScene {
 };
 
 // ============================================================================ setup kernels
+// (omega, apf) of a voxel from its droplet effective radius, as mca_atm_3d derives them on the host
+// (er3t/rtm/mca/mca_atm.py:291-303: scipy interp1d(..., fill_value='extrapolate') of ssa and asy against the table radii;
+// HG with the Mie asymmetry parameter).  fp64 without fused multiply-adds so that the float32 results equal numpy's.
+#define CER_MAX 64
+struct CerTab {
+    int n;
+    double ref[CER_MAX], ssa[CER_MAX], asy[CER_MAX];
+};
+__device__ __forceinline__ float2 cer_props(const CerTab& T, float ext, float cer) {
+    if (!(ext > 0.0f)) return make_float2(1.0f, -1.0f);              // clear voxel: conservative Rayleigh placeholder
+    const double x = double(cer);
+    int lo = 0, hi = T.n;                                            // first index with ref > x  (searchsorted side='right')
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (T.ref[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    const int i = min(T.n - 2, max(0, lo - 1));
+    const double t = __ddiv_rn(__dsub_rn(x, T.ref[i]), __dsub_rn(T.ref[i + 1], T.ref[i]));
+    const double o = __dadd_rn(T.ssa[i], __dmul_rn(t, __dsub_rn(T.ssa[i + 1], T.ssa[i])));
+    const double a = __dadd_rn(T.asy[i], __dmul_rn(t, __dsub_rn(T.asy[i + 1], T.asy[i])));
+    return make_float2(float(o), float(a));
+}
+
 // layout 0: [np3d][nz3][ny][nx] (x fastest, the byte order of the reference's binary file, mca_atm.py:383-388)
 // layout 1: numpy C order of the reference's in-memory arrays (nx, ny, nz3, np3d) (mca_atm.py:248-252): no host transpose
+// abs3 (optional, [nz3][ny][nx]): Atm_abst3d >= 0 becomes one more component with omega = 0 -- absorption as a collision
+// process (implicit capture) instead of the path integral used for the 1-D gas profile; same expectation
+// cer (optional, layout of ext, np3d == 1): (omega, apf) from the effective radius instead of omg / apf
 __global__ void pack_scene_kernel(const float* __restrict__ ext, const float* __restrict__ omg,
-                                  const float* __restrict__ apf, int np3d, int nx, int ny, int nz3, int layout,
+                                  const float* __restrict__ apf, const float* __restrict__ abs3, const float* __restrict__ cer,
+                                  const __grid_constant__ CerTab T, int np3d, int nx, int ny, int nz3, int layout,
                                   float* __restrict__ ext3tot, float2* __restrict__ prop3, float* __restrict__ ext3,
                                   int* __restrict__ bad) {
     const size_t nvox = size_t(nz3) * ny * nx;
@@ -159,15 +188,70 @@ __global__ void pack_scene_kernel(const float* __restrict__ ext, const float* __
         for (int c = 0; c < np3d; ++c) {
             const size_t src = layout == 0 ? size_t(c) * nvox + v : ((size_t(ix) * ny + iy) * nz3 + k) * np3d + c;
             const float e = ext[src];
-            const float o = omg[src];
-            const float a = apf[src];
-            if (!(e >= 0.0f) || !(o >= 0.0f && o <= 1.0f) || !isfinite(a)) atomicOr(bad, 1);
+            float2 pr;
+            if (cer) {
+                const float r = cer[src];
+                if (e > 0.0f && !isfinite(r)) atomicOr(bad, 1);
+                pr = cer_props(T, e, r);
+            } else pr = make_float2(omg[src], apf[src]);
+            if (!(e >= 0.0f) || !(pr.x >= 0.0f && pr.x <= 1.0f) || !isfinite(pr.y)) atomicOr(bad, 1);
             tot += e;
-            prop3[size_t(c) * nvox + v] = make_float2(o, a);
+            prop3[size_t(c) * nvox + v] = pr;
             if (ext3) ext3[size_t(c) * nvox + v] = e;
+        }
+        if (abs3) {
+            const float e = abs3[v];
+            if (!(e >= 0.0f) || !isfinite(e)) atomicOr(bad, 2);
+            tot += e;
+            prop3[size_t(np3d) * nvox + v] = make_float2(0.0f, 0.0f);
+            ext3[size_t(np3d) * nvox + v] = e;
         }
         ext3tot[v] = tot;
     }
+}
+
+// The common case -- ONE 3-D component handed over in the reference's in-memory order (nx, ny, nz3) -- as a tiled
+// transpose: a 32 x 32 tile of the (ix, k) plane of one iy is read with k fastest (the input's contiguous axis) and
+// written with ix fastest (the packed layout's), both as full 128-byte rows.  HBM streaming: 12 B read (or 8 B with
+// cer) + 12 B written per voxel.
+__global__ void __launch_bounds__(256) pack_scene_tiled_kernel(const float* __restrict__ ext, const float* __restrict__ omg,
+                                                               const float* __restrict__ apf, const float* __restrict__ cer,
+                                                               const __grid_constant__ CerTab T, int nx, int ny, int nz3,
+                                                               float* __restrict__ ext3tot, float2* __restrict__ prop3,
+                                                               int* __restrict__ bad) {
+    __shared__ float te[32][33];
+    __shared__ float2 tp[32][33];
+    const int k0 = blockIdx.x * 32, ix0 = blockIdx.y * 32, iy = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;           // (32, 8)
+    int isbad = 0;
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int ix = ix0 + ty + r, k = k0 + tx;
+        if (ix < nx && k < nz3) {
+            const size_t src = (size_t(ix) * ny + iy) * nz3 + k;
+            const float e = ext[src];
+            float2 pr;
+            if (cer) {
+                const float rr = cer[src];
+                if (e > 0.0f && !isfinite(rr)) isbad = 1;
+                pr = cer_props(T, e, rr);
+            } else pr = make_float2(omg[src], apf[src]);
+            if (!(e >= 0.0f) || !(pr.x >= 0.0f && pr.x <= 1.0f) || !isfinite(pr.y)) isbad = 1;
+            te[ty + r][tx] = e;
+            tp[ty + r][tx] = pr;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int k = k0 + ty + r, ix = ix0 + tx;
+        if (ix < nx && k < nz3) {
+            const size_t v = (size_t(k) * ny + iy) * nx + ix;
+            ext3tot[v] = te[tx][ty + r];
+            prop3[v] = tp[tx][ty + r];
+        }
+    }
+    if (isbad) atomicOr(bad, 1);
 }
 
 __global__ void majorant_kernel(const float* __restrict__ ext3tot, int nx, int ny, int nz3, int svx, int svy, int svz,
@@ -306,7 +390,7 @@ struct Photon {
     uint32_t rc0, rc1, rc2;   // Philox counter: global photon index (lo, hi), draw number
     float M;          // majorant of the cell in which the photon parked at a tentative collision
 };
-enum { FL_DIRECT = 1, FL_FROZEN = 2, FL_STALE = 4, FL_ABS = 8, FL_FSCALE = 16, FL_IN3 = 32, FL_EMPTY = 64 };
+enum { FL_DIRECT = 1, FL_FROZEN = 2, FL_STALE = 4, FL_ABS = 8, FL_FSCALE = 16, FL_IN3 = 32, FL_EMPTY = 64, FL_ESC = 128 };
 
 // pool record: NFIELD 32-bit words per slot, structure-of-arrays ([field][slot]) so that lanes touch distinct banks
 enum { F_X = 0, F_Y, F_Z, F_DX, F_DY, F_DZ, F_W, F_TAU, F_CELL, F_LAY, F_ORD, F_JOB, F_ZA, F_LEG, F_RC0, F_RC1, F_RC2, F_M, F_AUX, NFIELD };
@@ -1365,6 +1449,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         }
     }
 }
+#include "transport_v9.cuh"
 #undef ACC_ADD
 #undef CNT_ADD
 
@@ -1435,7 +1520,7 @@ struct Handle {
     // owned device memory
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3, runcode;
-    DevBuf st_e, st_o, st_a, f2c;
+    DevBuf st_e, st_o, st_a, st_b, f2c;
     DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
     DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
     DevBuf flux, rad, heat;
@@ -1446,8 +1531,32 @@ struct Handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     b200rt_stats stats_host{};
     bool ran = false;
+    bool inflight = false;       // a run has been launched and not yet waited for (one run in flight per handle)
     uint64_t launches = 0;
+    void* pin = nullptr;         // page-locked staging of the per-job tables (uploaded with cudaMemcpyAsync on the run's stream)
+    size_t pin_bytes = 0;
+    const void* attr_set[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // kernels whose smem attribute is set
+    size_t attr_smem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+// wait for the run in flight (if any) before its inputs, counters or tallies are touched again
+static cudaError_t drain(Handle* H) {
+    if (!H->inflight) return cudaSuccess;
+    H->inflight = false;
+    return cudaStreamSynchronize(H->last_stream);
+}
+
+// cudaFuncSetAttribute once per (kernel, shared-memory size)
+static cudaError_t set_smem_attr(Handle* H, const void* fn, size_t smem) {
+    for (int i = 0; i < 8; ++i)
+        if (H->attr_set[i] == fn && H->attr_smem[i] >= smem) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 8; ++i)
+        if (H->attr_set[i] == fn || H->attr_set[i] == nullptr) { H->attr_set[i] = fn; H->attr_smem[i] = smem; return cudaSuccess; }
+    H->attr_set[0] = fn; H->attr_smem[0] = smem;
+    return cudaSuccess;
+}
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -1537,13 +1646,14 @@ int b200rt_destroy(void* handle) {
     if (!H) return B200RT_ERR_ARG;
     cudaSetDevice(H->device);
     DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
-                     &H->st_e, &H->st_o, &H->st_a, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3, &H->runcode,
+                     &H->st_e, &H->st_o, &H->st_a, &H->st_b, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3, &H->runcode,
                      &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
                      &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
                      &H->flux, &H->rad, &H->heat};
     for (DevBuf* b : all) b->release();
     if (H->ev0) cudaEventDestroy(H->ev0);
     if (H->ev1) cudaEventDestroy(H->ev1);
+    if (H->pin) cudaFreeHost(H->pin);
     delete H;
     return B200RT_OK;
 }
@@ -1558,14 +1668,22 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     if (!H) return B200RT_ERR_ARG;
     if (!sc || !opt) return fail(H, B200RT_ERR_ARG, "null scene/options");
     CK(cudaSetDevice(H->device));
+    CK(drain(H));
     H->have_scene = false;
     // ------------------------------------------------ validate
     if (sc->nx < 1 || sc->ny < 1 || sc->nz < 1 || sc->np1d < 1) return fail(H, B200RT_ERR_ARG, "nx, ny, nz, np1d must be >= 1");
     if (!(sc->dx > 0) || !(sc->dy > 0)) return fail(H, B200RT_ERR_ARG, "dx, dy must be > 0");
     const int nz = sc->nz, nz3 = sc->nz3, iz0 = sc->iz3l - 1;
     if (nz3 < 0 || (nz3 > 0 && (iz0 < 0 || iz0 + nz3 > nz))) return fail(H, B200RT_ERR_ARG, "3-D block [iz3l, iz3l+nz3) exceeds the atmosphere (Atm_iz3l is 1-based)");
-    if (nz3 > 0 && (sc->np3d < 1 || !sc->ext3d || !sc->omg3d || !sc->apf3d)) return fail(H, B200RT_ERR_ARG, "3-D block without fields");
-    if (sc->abs3d) return fail(H, B200RT_ERR_ARG, "Atm_abst3d != 0 is not supported by the CUDA path yet");
+    const bool use_cer = nz3 > 0 && sc->cer3d != nullptr;
+    if (nz3 > 0 && (sc->np3d < 1 || !sc->ext3d || (!use_cer && (!sc->omg3d || !sc->apf3d)))) return fail(H, B200RT_ERR_ARG, "3-D block without fields");
+    if (use_cer) {
+        if (sc->np3d != 1) return fail(H, B200RT_ERR_ARG, "cer3d needs exactly one 3-D component");
+        if (sc->nref < 2 || sc->nref > CER_MAX || !sc->ref_tab || !sc->ssa_tab || !sc->asy_tab)
+            return fail(H, B200RT_ERR_ARG, "cer3d needs ref / ssa / asy tables of 2 ... 64 entries");
+        for (int i = 0; i + 1 < sc->nref; ++i)
+            if (!(sc->ref_tab[i + 1] > sc->ref_tab[i])) return fail(H, B200RT_ERR_ARG, "ref_tab must be strictly increasing");
+    }
     if (sc->nrad < 0 || sc->nrad > MAX_SENS) return fail(H, B200RT_ERR_ARG, "nrad out of range (max 16)");
     if (sc->layout3d != 0 && sc->layout3d != 1) return fail(H, B200RT_ERR_ARG, "layout3d must be 0 or 1");
     if (opt->nslab < 1) return fail(H, B200RT_ERR_ARG, "nslab must be >= 1");
@@ -1585,7 +1703,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
 
     DevScene& S = H->S;
     std::memset(&S, 0, sizeof(S));
-    S.nx = sc->nx; S.ny = sc->ny; S.nz = nz; S.iz0 = nz3 > 0 ? iz0 : 0; S.nz3 = nz3; S.np1d = sc->np1d; S.np3d = nz3 > 0 ? sc->np3d : 0;
+    S.nx = sc->nx; S.ny = sc->ny; S.nz = nz; S.iz0 = nz3 > 0 ? iz0 : 0; S.nz3 = nz3; S.np1d = sc->np1d; S.np3d = nz3 > 0 ? sc->np3d + (sc->abs3d ? 1 : 0) : 0;
     S.dx = float(sc->dx); S.dy = float(sc->dy); S.Lx = float(sc->dx * sc->nx); S.Ly = float(sc->dy * sc->ny);
     S.inv_dx = float(1.0 / sc->dx); S.inv_dy = float(1.0 / sc->dy);
     S.solver = opt->solver; S.target = opt->target;
@@ -1725,7 +1843,8 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     if (nz3 > 0) {
         const size_t nvox = size_t(nz3) * sc->ny * sc->nx;
         const size_t nall = nvox * sc->np3d;
-        if ((rc = dev_alloc(H, H->ext3tot, nvox * 4)) || (rc = dev_alloc(H, H->prop3, nall * 8)) ||
+        const int np3e = S.np3d;                                   // + 1 when Atm_abst3d is present
+        if ((rc = dev_alloc(H, H->ext3tot, nvox * 4)) || (rc = dev_alloc(H, H->prop3, nvox * np3e * 8)) ||
             (rc = dev_alloc(H, H->maj, size_t(S.ncx) * S.ncy * S.ncz * 4)) || (rc = dev_alloc(H, H->empty3, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1))) ||
             (rc = dev_alloc(H, H->runcode, size_t(S.nCx) * S.nCy * (gz_lo.size() - 1) * 4)) || (rc = dev_alloc(H, H->tu3, (nvox + size_t(sc->nx) * sc->ny) * 4)) ||
             (rc = dev_alloc(H, H->flag, 16)))
@@ -1738,21 +1857,48 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
             CK(cudaMemcpy(H->st_e.p, sc->ext3d, nall * 4, cudaMemcpyDefault));
             de = (const float*)H->st_e.p;
         }
-        if (!is_device_ptr(sc->omg3d)) {
-            if ((rc = dev_alloc(H, H->st_o, nall * 4))) return rc;
-            CK(cudaMemcpy(H->st_o.p, sc->omg3d, nall * 4, cudaMemcpyDefault));
-            dom = (const float*)H->st_o.p;
+        const float* dcer = nullptr;
+        CerTab ctab;
+        ctab.n = 0;
+        if (use_cer) {
+            dom = da = nullptr;
+            dcer = sc->cer3d;
+            if (!is_device_ptr(sc->cer3d)) {
+                if ((rc = dev_alloc(H, H->st_o, nall * 4))) return rc;
+                CK(cudaMemcpy(H->st_o.p, sc->cer3d, nall * 4, cudaMemcpyDefault));
+                dcer = (const float*)H->st_o.p;
+            }
+            ctab.n = sc->nref;
+            for (int i = 0; i < sc->nref; ++i) { ctab.ref[i] = sc->ref_tab[i]; ctab.ssa[i] = sc->ssa_tab[i]; ctab.asy[i] = sc->asy_tab[i]; }
+        } else {
+            if (!is_device_ptr(sc->omg3d)) {
+                if ((rc = dev_alloc(H, H->st_o, nall * 4))) return rc;
+                CK(cudaMemcpy(H->st_o.p, sc->omg3d, nall * 4, cudaMemcpyDefault));
+                dom = (const float*)H->st_o.p;
+            }
+            if (!is_device_ptr(sc->apf3d)) {
+                if ((rc = dev_alloc(H, H->st_a, nall * 4))) return rc;
+                CK(cudaMemcpy(H->st_a.p, sc->apf3d, nall * 4, cudaMemcpyDefault));
+                da = (const float*)H->st_a.p;
+            }
         }
-        if (!is_device_ptr(sc->apf3d)) {
-            if ((rc = dev_alloc(H, H->st_a, nall * 4))) return rc;
-            CK(cudaMemcpy(H->st_a.p, sc->apf3d, nall * 4, cudaMemcpyDefault));
-            da = (const float*)H->st_a.p;
+        const float* dabs = sc->abs3d;
+        if (sc->abs3d && !is_device_ptr(sc->abs3d)) {
+            if ((rc = dev_alloc(H, H->st_b, nvox * 4))) return rc;
+            CK(cudaMemcpy(H->st_b.p, sc->abs3d, nvox * 4, cudaMemcpyDefault));
+            dabs = (const float*)H->st_b.p;
         }
-        if (sc->np3d > 1) { if ((rc = dev_alloc(H, H->ext3, nall * 4))) return rc; }
+        if (np3e > 1) { if ((rc = dev_alloc(H, H->ext3, nvox * np3e * 4))) return rc; }
         CK(cudaMemset(H->flag.p, 0, 16));
-        const int nb = int(std::min<size_t>((nvox + 255) / 256, size_t(H->numSM) * 16));
-        pack_scene_kernel<<<nb, 256>>>(de, dom, da, sc->np3d, sc->nx, sc->ny, nz3, sc->layout3d, (float*)H->ext3tot.p, (float2*)H->prop3.p,
-                                       sc->np3d > 1 ? (float*)H->ext3.p : nullptr, (int*)H->flag.p);
+        if (sc->layout3d == 1 && np3e == 1 && sc->ny <= 65535 && (sc->nx + 31) / 32 <= 65535) {
+            const dim3 tg((nz3 + 31) / 32, (sc->nx + 31) / 32, sc->ny);
+            pack_scene_tiled_kernel<<<tg, dim3(32, 8)>>>(de, dom, da, dcer, ctab, sc->nx, sc->ny, nz3, (float*)H->ext3tot.p, (float2*)H->prop3.p,
+                                                         (int*)H->flag.p);
+        } else {
+            const int nb = int(std::min<size_t>((nvox + 255) / 256, size_t(H->numSM) * 16));
+            pack_scene_kernel<<<nb, 256>>>(de, dom, da, dabs, dcer, ctab, sc->np3d, sc->nx, sc->ny, nz3, sc->layout3d, (float*)H->ext3tot.p,
+                                           (float2*)H->prop3.p, np3e > 1 ? (float*)H->ext3.p : nullptr, (int*)H->flag.p);
+        }
         const int ncell = S.ncx * S.ncy * S.ncz;
         majorant_kernel<<<(ncell + 127) / 128, 128>>>((const float*)H->ext3tot.p, sc->nx, sc->ny, nz3, svx, svy, svz, S.ncx, S.ncy, S.ncz, (float*)H->maj.p);
         const int nC = S.nCx * S.nCy * int(gz_lo.size() - 1);
@@ -1768,6 +1914,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         CK(cudaDeviceSynchronize());
         int bad = 0;
         CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad & 2) return fail(H, B200RT_ERR_ARG, "Atm_abst3d must be finite and >= 0 (a negative absorption perturbation is not supported)");
         if (bad) return fail(H, B200RT_ERR_ARG, "3-D field out of range (need ext >= 0, 0 <= omg <= 1, finite apf)");
         S.ext3tot = (const float*)H->ext3tot.p; S.prop3 = (const float2*)H->prop3.p; S.ext3 = (const float*)H->ext3.p;
         S.maj = (const float*)H->maj.p; S.tu3 = (const float*)H->tu3.p; S.empty3 = (const unsigned char*)H->empty3.p;
@@ -1817,10 +1964,18 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
         std::vector<float> sp;
         if ((rc = fetch_host(H, sc->sfc_type, sn, st))) return rc;
         if ((rc = fetch_host(H, sc->sfc_param, sn * 5, sp))) return rc;
+        for (size_t i = 0; i < sn * 5; ++i)
+            if (!std::isfinite(sp[i])) return fail(H, B200RT_ERR_ARG, "non-finite surface parameter");
         for (size_t i = 0; i < sn; ++i) {
             if (st[i] != B200RT_SFC_LAMBERT && st[i] != B200RT_SFC_DSM && st[i] != B200RT_SFC_LSRT)
                 return fail(H, B200RT_ERR_ARG, "unsupported surface type (1 Lambertian, 2 DSM, 4 LSRT)");
-            if (!std::isfinite(sp[i])) return fail(H, B200RT_ERR_ARG, "non-finite surface parameter");
+            // parameter ranges (mca_sfc.py:89-133): albedo-like values in [0, 1], slope variance > 0
+            if (st[i] == B200RT_SFC_LAMBERT && !(sp[i] >= 0.f && sp[i] <= 1.f)) return fail(H, B200RT_ERR_ARG, "Lambertian albedo outside [0, 1]");
+            if (st[i] == B200RT_SFC_DSM) {
+                if (!(sp[i] >= 0.f && sp[i] <= 1.f) || !(sp[sn + i] >= 0.f && sp[sn + i] <= 1.f))
+                    return fail(H, B200RT_ERR_ARG, "DSM surface: diffuse albedo and diffuse fraction must lie in [0, 1]");
+                if (!(sp[4 * sn + i] > 0.f)) return fail(H, B200RT_ERR_ARG, "DSM surface: slope variance must be > 0");
+            }
         }
         if ((rc = upload(H, H->sfc_type, st)) || (rc = upload(H, H->sfc_param, sp))) return rc;
         S.sfc_nx = sc->sfc_nx; S.sfc_ny = sc->sfc_ny;
@@ -1901,8 +2056,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     H->k_cam = false;
     for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
     H->pool_slots = opt->pool_slots;
-    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 80 && H->pool_slots != 96 && H->pool_slots != 128)
-        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 32, 64, 80, 96 or 128");
+    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 80 && H->pool_slots != 96 && H->pool_slots != 128 &&
+        H->pool_slots != 1024 && H->pool_slots != 1536 && H->pool_slots != 2048)
+        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 1024, 1536 or 2048 (per block) or 32 ... 128 (per warp, v8 kernel)");
     H->opt = *opt;
     H->have_scene = true;
     H->ran = false;
@@ -1916,12 +2072,28 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     if (!jobs || njob < 1) return fail(H, B200RT_ERR_ARG, "no jobs");
     if (njob > 65535) return fail(H, B200RT_ERR_ARG, "at most 65535 jobs per run");
     CK(cudaSetDevice(H->device));
+    CK(drain(H));                 // one run in flight per handle: the previous one still reads the job tables and counters
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     DevScene& S = H->S;
     const int nz = S.nz;
-    std::vector<DevJob> dj(njob);
-    std::vector<float> jabs(size_t(njob) * nz, 0.f), jcabs(size_t(njob) * (nz + 1), 0.f);
-    std::vector<double> jfs(size_t(njob) * (nz + 1), 1.0);
+    // per-job tables are built in page-locked memory and uploaded asynchronously on the caller's stream
+    const size_t b_jobs = size_t(njob) * sizeof(DevJob), b_abs = size_t(njob) * nz * 4, b_cabs = size_t(njob) * (nz + 1) * 4,
+                 b_fs = size_t(njob) * (nz + 1) * 8;
+    const size_t o_jobs = 0, o_fs = (b_jobs + 15) & ~size_t(15), o_abs = o_fs + ((b_fs + 15) & ~size_t(15)), o_cabs = o_abs + ((b_abs + 15) & ~size_t(15));
+    const size_t need = o_cabs + b_cabs + 16;
+    if (need > H->pin_bytes) {
+        if (H->pin) cudaFreeHost(H->pin);
+        H->pin = nullptr; H->pin_bytes = 0;
+        CK(cudaMallocHost(&H->pin, 2 * need));
+        H->pin_bytes = 2 * need;
+    }
+    char* pin = static_cast<char*>(H->pin);
+    DevJob* dj = reinterpret_cast<DevJob*>(pin + o_jobs);
+    double* jfs = reinterpret_cast<double*>(pin + o_fs);
+    float* jabs = reinterpret_cast<float*>(pin + o_abs);
+    float* jcabs = reinterpret_cast<float*>(pin + o_cabs);
+    std::memset(jabs, 0, b_abs);
+    std::memset(jcabs, 0, b_cabs);
     unsigned long long acc = 0;
     for (int j = 0; j < njob; ++j) {
         const b200rt_job& q = jobs[j];
@@ -1935,7 +2107,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
         d.norm = q.nphot > 0 ? double(S.mu0) * H->src_flx / double(q.nphot) : 0.0;
         d.rad_fac = d.norm * q.rad_scale;
         d.slab = q.slab;
-        d.has_abs = 0; d.has_fscale = 0;
+        d.has_abs = 0; d.has_fscale = 0; d._pad = 0;
         if (q.abs1d) {
             double c = 0;
             for (int i = 0; i < nz; ++i) {
@@ -1956,9 +2128,13 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
         d.heat_off = (unsigned long long)q.slab * (unsigned long long)nz * (unsigned long long)(S.nx) * (unsigned long long)(S.ny);
     }
     int rc;
-    if ((rc = upload(H, H->jobs, dj)) || (rc = upload(H, H->job_abs, jabs)) || (rc = upload(H, H->job_cabs, jcabs)) ||
-        (rc = upload(H, H->job_fscale, jfs)))
+    if ((rc = dev_alloc(H, H->jobs, b_jobs)) || (rc = dev_alloc(H, H->job_abs, b_abs)) || (rc = dev_alloc(H, H->job_cabs, b_cabs)) ||
+        (rc = dev_alloc(H, H->job_fscale, b_fs)))
         return rc;
+    CK(cudaMemcpyAsync(H->jobs.p, dj, b_jobs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(H->job_abs.p, jabs, b_abs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(H->job_cabs.p, jcabs, b_cabs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(H->job_fscale.p, jfs, b_fs, cudaMemcpyHostToDevice, st));
     S.njob = njob; S.jobs = (const DevJob*)H->jobs.p; S.job_abs = (const float*)H->job_abs.p;
     S.job_cabs = (const float*)H->job_cabs.p; S.job_fscale = (const double*)H->job_fscale.p;
     S.nphot_local = acc;
@@ -1974,13 +2150,37 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     // launch shape: the per-warp photon pools decide how many blocks fit on an SM (shared memory), see DESIGN.md
     int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : RT_TPB;
     tpb = std::min(RT_TPB, std::max(32, (tpb / 32) * 32));
-    const int np = H->pool_slots > 0 ? H->pool_slots : 96;
+    const char* kenv = getenv("B200RT_KERNEL");
+    const int kver = kenv ? atoi(kenv) : (H->opt.kernel == 8 ? 8 : 9);
+    if (kver == 9) {
+        // role-specialised kernel: one block per SM, block-level photon pool (transport_v9.cuh)
+        int npb = H->pool_slots >= 1024 ? H->pool_slots : V9_NPB;
+        if (const char* e = getenv("B200RT_V9_POOL")) npb = atoi(e);
+#ifdef V9_ALL_POOLS
+        if (npb != 1024 && npb != 2048) npb = V9_NPB;
+#else
+        npb = V9_NPB;
+#endif
+        const bool uz = S.uz_ok != 0;
+        transport_fn9 kern = pick_v9(H->k_pl, H->k_fz, H->k_cam, uz, npb);
+        const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(V9_NT) * 8 + size_t(V9_POOL_WORDS(npb)) * 4 +
+                            8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
+        if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pool + 1-D tables exceed shared memory; lower pool_slots");
+        CK(set_smem_attr(H, (const void*)kern, smem));
+        const unsigned long long want = (acc + npb - 1) / npb;
+        const int grid = int(std::min<unsigned long long>((unsigned long long)H->numSM, std::max<unsigned long long>(1, want)));
+        CK(cudaEventRecord(H->ev0, st));
+        kern<<<grid, V9_NT, smem, st>>>(S);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(H->ev1, st));
+    } else {
+    const int np = H->pool_slots > 0 && H->pool_slots <= 128 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    CK(set_smem_attr(H, (const void*)kern, smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));
     if (bps < 1) return fail(H, B200RT_ERR_CUDA, "transport kernel does not fit on an SM");
     if (H->opt.blocks_per_sm > 0) bps = std::min(bps, H->opt.blocks_per_sm);
@@ -1990,8 +2190,10 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     kern<<<grid, tpb, smem, st>>>(S);
     CK(cudaGetLastError());
     CK(cudaEventRecord(H->ev1, st));
+    }
     H->last_stream = st;
     H->ran = true;
+    H->inflight = true;
     H->launches = 1;
     return B200RT_OK;
 }
@@ -2010,6 +2212,7 @@ int b200rt_sync(void* handle) {
     H->launches = 1 + (H->nflux ? 1 : 0) + (H->nrad ? 1 : 0) + (H->nheat ? 1 : 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
+    H->inflight = false;
     int bad = 0;
     CK(cudaMemcpy(&bad, H->flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     DevStats ds;
@@ -2025,6 +2228,7 @@ int b200rt_sync(void* handle) {
     o.bytes_alg = 4.0 * double(ds.n_cell) + 4.0 * double(ds.n_tent) + 8.0 * double(ds.n_coll) + 4.0 * double(ds.n_le_visit) +
                   8.0 * double(ds.n_tally) + 2.0 * 8.0 * double(H->nflux + H->nrad + H->nheat);
     o.launches = H->launches;
+    if (ds.hang) return fail(H, B200RT_ERR_STATE, "transport kernel watchdog: a warp idled for seconds (internal queue protocol error)");
     if (bad) return fail(H, B200RT_ERR_NUMERIC, "NaN/Inf found in tallies");
     return B200RT_OK;
 }
@@ -2034,7 +2238,7 @@ static int read_any(Handle* H, const DevBuf& b, size_t n, double* dst, int64_t c
     if (n == 0) return fail(H, B200RT_ERR_STATE, std::string(what) + " was not part of the target");
     if (!dst || count < 0 || size_t(count) < n) return fail(H, B200RT_ERR_ARG, std::string("destination too small for ") + what);
     CK(cudaSetDevice(H->device));
-    CK(cudaStreamSynchronize(H->last_stream));
+    CK(drain(H));
     CK(cudaMemcpy(dst, b.p, n * 8, cudaMemcpyDefault));
     return B200RT_OK;
 }

@@ -19,6 +19,34 @@ from er3t_b200.util import cal_mol_ext, get_lay_index, host_zeros
 __all__ = ['mca_atm_1d', 'mca_atm_3d']
 
 
+class _LazyArray:
+    """A numpy array that is computed the first time somebody looks at it (np.asarray, indexing, .shape ...).
+    `mca_atm_3d(device_props=True)` uses it for the fields the GPU derives itself, so that the namelist payload of the
+    reference (er3t/rtm/mca/mca_atm.py:324-337) stays available without being paid for on every run."""
+
+    def __init__(self, fn, shape, dtype=np.float32):
+        self._fn, self._val, self.shape, self.dtype = fn, None, tuple(shape), np.dtype(dtype)
+        self.ndim = len(self.shape)
+
+    def get(self):
+        if self._val is None:
+            self._val = self._fn()
+        return self._val
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.get()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __getitem__(self, key):
+        return self.get()[key]
+
+    def __setitem__(self, key, val):
+        self.get()[key] = val
+
+    def __getattr__(self, name):           # anything else behaves like the array
+        return getattr(self.get(), name)
+
+
 class mca_atm_1d:
 
     """
@@ -101,7 +129,13 @@ class mca_atm_3d:
     ID = 'MCARaTS 3D Atmosphere'
 
     def __init__(self, atm_obj=None, cld_obj=None, pha_obj=None, fname=None, overwrite=True, force=False,
-                 verbose=False, quiet=False):
+                 verbose=False, quiet=False, *, device_props=False):
+        """device_props=True (new, keyword only): with a Mie `pha_obj`, single-scattering albedo and asymmetry parameter
+        of the cloudy voxels are NOT interpolated on the host (mca_atm.py:291-303, 0.1-10 s at config 2); the effective
+        radius field and the (ref, ssa, asy) tables are handed to the solver, whose scene-packing kernel derives the
+        same float32 values on the GPU (include/b200rt.h, scene.cer3d).  `nml['Atm_omgp3d']['data']` etc. remain
+        available as lazily evaluated arrays."""
+        self.device_props = bool(device_props)
         self.overwrite = overwrite
         self.verbose = verbose
         self.quiet = quiet
@@ -141,6 +175,12 @@ class mca_atm_3d:
 
         ext_in = cld['extinction']['data']
         ext_in = ext_in.data if isinstance(ext_in, np.ma.MaskedArray) else np.asarray(ext_in)
+        pid = None if self.pha is None else self.pha.data['id']['data'].lower()
+        self.cer3d = None
+        self.cer_tables = None
+        if self.device_props and pid == 'mie':
+            self._pre_device(cld, atm, lay_index, ext_in, nx, ny, nz3, iz3l)
+            return
         atm_tmp = np.asarray(cld['temperature']['data'], dtype=np.float32) - atm['temperature']['data'][lay_index].astype(np.float32)[None, None, :]
         atm_abs = np.zeros((nx, ny, nz3, 1), dtype=np.float32)
         # the three fields the solver reads live in page-locked memory when a GPU is present (fast H2D)
@@ -169,6 +209,40 @@ class mca_atm_3d:
                 atm_omg[logic_cld, 0] = _interp_extrap(c, ref, self.pha.data['ssa']['data'])
                 atm_apf[logic_cld, 0] = _interp_extrap(c, ref, self.pha.data['asy']['data'])
 
+        self._fill_nml(cld, nz3, iz3l, atm_tmp, atm_abs, atm_ext, atm_omg, atm_apf)
+
+    def _pre_device(self, cld, atm, lay_index, ext_in, nx, ny, nz3, iz3l):
+        """device_props: only extinction and effective radius are touched on the host (two float32 copies into
+        page-locked memory); omega / apf / temperature deviation are lazy."""
+        cer = cld['cer']['data']
+        cer = cer.data if isinstance(cer, np.ma.MaskedArray) else np.asarray(cer)
+        atm_ext = host_zeros((nx, ny, nz3, 1), np.float32)
+        atm_ext[..., 0] = ext_in[:, :, :nz3]
+        cer3 = host_zeros((nx, ny, nz3, 1), np.float32)
+        cer3[..., 0] = cer[:, :, :nz3]
+        self.cer3d = cer3
+        ref = np.ascontiguousarray(self.pha.data['ref']['data'], dtype=np.float64)
+        ssa = np.ascontiguousarray(self.pha.data['ssa']['data'], dtype=np.float64)
+        asy = np.ascontiguousarray(self.pha.data['asy']['data'], dtype=np.float64)
+        self.cer_tables = (ref, ssa, asy)
+
+        def props(which):
+            def f():
+                out = np.full((nx, ny, nz3, 1), 1.0 if which == 0 else -1.0, dtype=np.float32)
+                m = atm_ext[..., 0] > 0.0
+                # the float32 effective radius the GPU sees, interpolated in float64 like mca_atm.py:291-303
+                out[m, 0] = _interp_extrap(cer3[..., 0][m].astype(np.float64), ref, ssa if which == 0 else asy)
+                return out
+            return f
+
+        def tmpa():
+            return np.asarray(cld['temperature']['data'], dtype=np.float32) - atm['temperature']['data'][lay_index].astype(np.float32)[None, None, :]
+
+        shp = (nx, ny, nz3, 1)
+        self._fill_nml(cld, nz3, iz3l, _LazyArray(tmpa, (nx, ny, nz3)), _LazyArray(lambda: np.zeros(shp, dtype=np.float32), shp), atm_ext,
+                       _LazyArray(props(0), shp), _LazyArray(props(1), shp))
+
+    def _fill_nml(self, cld, nz3, iz3l, atm_tmp, atm_abs, atm_ext, atm_omg, atm_apf):
         self.nml = {}
         self.nml['Atm_nx'] = copy.deepcopy(cld['nx'])
         self.nml['Atm_ny'] = copy.deepcopy(cld['ny'])
@@ -180,7 +254,7 @@ class mca_atm_3d:
         # that results match "MCARaTS as driven by er3t"; mcarats_ng(..., iz3l_fix=True) undoes it.
         self.nml['Atm_iz3l'] = {'data': iz3l + 1, 'unit': 'N/A', 'name': 'layer index of first 3D layer'}
         self.nml['Atm_tmpa3d'] = {'data': atm_tmp, 'units': 'K', 'name': 'Temperature deviation'}
-        self.nml['Atm_abst3d'] = {'data': atm_abs, 'units': '/m', 'name': 'Absorption coefficients deviation', 'all_zero': True}
+        self.nml['Atm_abst3d'] = {'data': atm_abs, 'units': '/m', 'name': 'Absorption coefficients deviation'}
         self.nml['Atm_extp3d'] = {'data': atm_ext, 'units': '/m', 'name': 'Extinction coefficients'}
         self.nml['Atm_omgp3d'] = {'data': atm_omg, 'units': 'N/A', 'name': 'Single scattering Albedo'}
         self.nml['Atm_apfp3d'] = {'data': atm_apf, 'units': 'N/A', 'name': 'Phase function'}

@@ -275,16 +275,19 @@ class mca_out_ng:
         except ImportError:
             h5py = None
         if h5py is not None:
+            # call for call what the reference asks of h5py (mca_out.py:216-231; pinned by tests/golden/h5_dump_calls.json):
+            # every ndarray -- 0-d included -- becomes a gzip-9 chunked dataset, scalars plain members, `dims_info` an
+            # array of byte strings (np.string_ of the list), the other attributes as they are
             with h5py.File(self.fname, 'w') as f:
                 g = f.create_group(mode)
                 for key, item in self.data.items():
-                    if isinstance(item['data'], np.ndarray) and item['data'].ndim > 0:
+                    if isinstance(item['data'], np.ndarray):
                         g.create_dataset(key, data=item['data'], compression='gzip', compression_opts=9, chunks=True)
                     else:
                         g[key] = item['data']
                     for k0, v0 in item.items():
                         if k0 != 'data':
-                            g[key].attrs[k0] = np.bytes_(str(v0)) if k0 == 'dims_info' else v0
+                            g[key].attrs[k0] = np.bytes_(v0) if k0 == 'dims_info' else v0
         else:
             flat = {}
             for key, item in self.data.items():

@@ -42,9 +42,13 @@ class mca_run:
         if run:
             self.run()
 
-    def run(self):
+    def launch(self):
+        """upload the scene and trace all jobs (synchronous); the tallies stay on the device"""
         self.solver.upload_scene(self.scene, self.options)
         self.solver.run(self.jobs)
+
+    def run(self):
+        self.launch()
         self.results = self.solver.results()
         return self.results
 

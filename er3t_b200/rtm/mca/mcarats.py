@@ -24,7 +24,8 @@ import time
 import numpy as np
 
 from er3t_b200 import abi
-from er3t_b200.solver import Solver
+from er3t_b200.solver import Solver   # noqa: F401  (re-exported for callers that build their own handle)
+from .mca_run import mca_run
 from er3t_b200.util import add_reference
 from .mca_inp import mca_inp_file, DEFAULTS
 from .mca_out import cal_factors, write_mca_out_raw
@@ -109,7 +110,8 @@ class mcarats_ng:
         self.Nrun = Nrun
         self.seed = seed
         self.device = device
-        self.keep_raw = raw
+        # write_files asks for MCARaTS-style per-job .bin/.ctl outputs: they only exist for un-fused (raw) slabs
+        self.keep_raw = raw or write_files
         self.iz3l_fix = iz3l_fix
         self.supervoxel = supervoxel
         self.shard = shard if shard is not None else (0, 1)
@@ -317,6 +319,9 @@ class mcarats_ng:
         nz = zgrd.size - 1
         np1d = int(n0.get('Atm_np1d', 1))
         ext1d = np.stack([np.asarray(n0['Atm_ext1d(1:, %d)' % (k + 1)], dtype=np.float64) for k in range(np1d)])
+        if 'Atm_fext1d' in n0:
+            # Atm_fext1d(KNP1D): scaling factor for Atm_ext1d (mca_inp.py:232); er3t never sets it (default 1)
+            ext1d = ext1d * np.broadcast_to(np.asarray(n0['Atm_fext1d'], dtype=np.float64), (np1d,))[:, None]
         omg1d = np.stack([np.asarray(n0['Atm_omg1d(1:, %d)' % (k + 1)], dtype=np.float64) for k in range(np1d)])
         apf1d = np.stack([np.asarray(n0['Atm_apf1d(1:, %d)' % (k + 1)], dtype=np.float64) for k in range(np1d)])
         if ext1d.shape[1] != nz:
@@ -328,8 +333,29 @@ class mcarats_ng:
             if self.iz3l_fix:
                 iz3l -= 1
             kw.update(nx=int(a3['Atm_nx']['data']), ny=int(a3['Atm_ny']['data']), dx=float(a3['Atm_dx']['data']), dy=float(a3['Atm_dy']['data']),
-                      iz3l=iz3l, ext3d=a3['Atm_extp3d']['data'], omg3d=a3['Atm_omgp3d']['data'], apf3d=a3['Atm_apfp3d']['data'],
-                      abs3d=None if a3['Atm_abst3d'].get('all_zero') else a3['Atm_abst3d']['data'])
+                      iz3l=iz3l, ext3d=a3['Atm_extp3d']['data'])
+            a3obj = self.atm_3ds[-1]
+            if getattr(a3obj, 'cer3d', None) is not None and int(a3['Atm_np3d']['data']) == 1:
+                # mca_atm_3d(device_props=True): the GPU derives (omega, apf) from the effective radius while packing the scene
+                kw.update(cer3d=a3obj.cer3d, cer_tables=a3obj.cer_tables)
+            else:
+                kw.update(omg3d=a3['Atm_omgp3d']['data'], apf3d=a3['Atm_apfp3d']['data'])
+            # Atm_abst3d: always looked at (a caller may have filled the array in place); only lazily created zeros
+            # that nobody has touched are skipped
+            b3d = a3['Atm_abst3d']['data']
+            if hasattr(b3d, '_fn') and b3d._val is None:
+                b3d = None                                    # lazy zeros nobody has touched
+            elif b3d is not None and not np.any(np.asarray(b3d)):
+                b3d = None
+            kw.update(abs3d=b3d)
+            fe3, fa3 = self.nml[0].get('Atm_fext3d', 1.0), self.nml[0].get('Atm_fabs3d', 1.0)
+            if np.any(np.asarray(fe3) != 1.0):
+                # Atm_fext3d(KNP3D): scaling factor for the 3-D extinction (mca_inp.py:233)
+                e3s = np.asarray(kw['ext3d'], dtype=np.float32)
+                e3s = e3s[..., np.newaxis] if e3s.ndim == 3 else e3s
+                kw['ext3d'] = e3s * np.broadcast_to(np.asarray(fe3, dtype=np.float32), (e3s.shape[3],))
+            if kw['abs3d'] is not None and float(fa3) != 1.0:
+                kw['abs3d'] = np.asarray(kw['abs3d'], dtype=np.float32) * np.float32(fa3)
         if self.sca is not None and int(n0.get('Sca_npf', 0)) > 0:
             kw.update(ang=self.sca.pha.data['ang']['data'], pha=self.sca.pha.data['pha']['data'])
         if self.sfc_2d:
@@ -381,7 +407,6 @@ class mcarats_ng:
         self.fuse = fuse
         if fuse:
             f_lev, _ = cal_factors(self.date, self.abs, nz + 1, Ng)       # flux levels
-            f_lay, _ = cal_factors(self.date, self.abs, nz, Ng)           # heating (layers)
             f_rad, _ = cal_factors(self.date, self.abs, 1, Ng)
             nslab = Nrun
         else:
@@ -394,7 +419,10 @@ class mcarats_ng:
                 seeds.append(int(self.seeds[ir, ig]))
                 slabs.append(ir if fuse else ir * Ng + ig)
                 key = 'Atm_abs1d(1:, 1)'
-                abs1d.append(np.asarray(self.nml[ig][key], dtype=np.float64) if key in self.nml[ig] else None)
+                a1 = np.asarray(self.nml[ig][key], dtype=np.float64) if key in self.nml[ig] else None
+                if a1 is not None and 'Atm_fabs1d' in self.nml[ig]:
+                    a1 = a1 * float(self.nml[ig]['Atm_fabs1d'])          # scaling factor for Atm_abs1d (mca_inp.py:234)
+                abs1d.append(a1)
                 fsc.append(f_lev[:, ig].astype(np.float64) if fuse else None)
                 rsc.append(float(f_rad[0, ig]) if fuse else 1.0)
         wmin = DEFAULTS['Pho_wmin'] if self._wmin is None else self._wmin
@@ -407,20 +435,18 @@ class mcarats_ng:
             # device-resident path separately from the host-side packing
             self.fused = {}
             return
-        own = self._solver_obj is None
-        sol = Solver(device=self.device) if own else self._solver_obj
+        # the reference hands the job list to `mca_run` (mcarats.py:468); so does this class -- one launch instead of a pool
+        runner = mca_run(scene, opt, nphot, seeds, slabs, abs1d=abs1d, flx_scale=fsc, rad_scale=rsc, device=self.device,
+                         solver_obj=self._solver_obj, Ncpu=self.Ncpu, mp_mode=self.mp_mode, quiet=True, run=False)
         try:
-            sol.upload_scene(scene, opt)
-            jobs, keep = abi.make_jobs(nphot, seeds, slabs, abs1d=abs1d, flx_scale=fsc, rad_scale=rsc)
-            self.h2d_bytes = scene.nbytes() + sum(a.nbytes for a in keep)
-            sol.run(jobs)
+            self.h2d_bytes = scene.nbytes() + sum(a.nbytes for a in runner._keep)
+            runner.launch()
             if self.reduce is not None:
-                res = self.reduce(sol)          # multi-GPU: all-reduce of the tallies (er3t_b200.dist.allreduce_results)
+                res = self.reduce(runner.solver)     # multi-GPU: all-reduce of the tallies (er3t_b200.dist.allreduce_results)
             else:
-                res = sol.results()
+                res = runner.solver.results()
         finally:
-            if own:
-                sol.close()
+            runner.close()
         self.stats = res['stats']
         self._store(res, scene, nslab, fuse)
 
@@ -482,32 +508,25 @@ class mcarats_ng:
                 raise OSError('Error [mcarats_ng]: Missing some output files.')
 
     def print_info(self):
-        print('╭────────────────────────────────────────────────────────╮')
-        print('                 General Information                      ')
-        print('               Simulation : %s %s' % (self.solver, self.target.title()))
-        print('               Wavelength : %s' % (self.wvl_info))
-        print('               Date (DOY) : %s (%d)' % (self.date.strftime('%Y-%m-%d'), self.date.timetuple().tm_yday))
-        print('       Solar Zenith Angle : %.4f° (0 at local zenith)' % self.solar_zenith_angle)
-        print('      Solar Azimuth Angle : %.4f° (0 at north; 90° at east)' % self.solar_azimuth_angle)
+        """One-paragraph summary of the run (the reference prints a boxed banner here, mcarats.py:486-523)."""
+        rows = [('simulation', '%s %s' % (self.solver, self.target)),
+                ('wavelength', str(self.wvl_info)),
+                ('date', '%s (day of year %d)' % (self.date.strftime('%Y-%m-%d'), self.date.timetuple().tm_yday)),
+                ('sun', 'zenith %.4f deg, azimuth %.4f deg (from north, clockwise)' % (self.solar_zenith_angle, self.solar_azimuth_angle))]
         if self.target == 'radiance':
-            if self.sensor_zenith_angle < 90.0:
-                print('      Sensor Zenith Angle : %.4f° (looking down, 0 straight down)' % self.sensor_zenith_angle)
-            else:
-                print('      Sensor Zenith Angle : %.4f° (looking up, 180° straight up)' % self.sensor_zenith_angle)
-            print('     Sensor Azimuth Angle : %.4f° (0 at north; 90° at east)' % self.sensor_azimuth_angle)
-            print('          Sensor Altitude : %.1f km' % (self.sensor_altitude / 1000.0))
-        if not self.sfc_2d:
-            print('           Surface Albedo : %.2f' % self.surface_albedo)
-        else:
-            print('           Surface Albedo : 2D domain')
-        print('           Phase Function : %s' % ('Henyey-Greenstein' if self.sca is None else self.sca.pha.ID))
-        if (self.Nx > 1) | (self.Ny > 1):
-            print('     Domain Size (Nx, Ny) : (%d, %d)' % (self.Nx, self.Ny))
-            print('      Pixel Res. (dx, dy) : (%.2f km, %.2f km)' % (self.dx / 1000.0, self.dy / 1000.0))
-        print('  Number of Photons / Set : %.1e (%s over %d g)' % (self.photons_per_set, self.np_mode, self.Ng))
-        print('           Number of Runs : %s (g) * %d (set)' % (self.Ng, self.Nrun))
-        print('                   Solver : in-process CUDA (sm_100a), device %d' % self.device)
-        print('╰────────────────────────────────────────────────────────╯')
+            rows.append(('sensor', 'zenith %.4f deg (%s), azimuth %.4f deg, altitude %.1f km' % (
+                self.sensor_zenith_angle, 'looking down' if self.sensor_zenith_angle < 90.0 else 'looking up',
+                self.sensor_azimuth_angle, self.sensor_altitude / 1000.0)))
+        rows.append(('surface', '2-D map' if self.sfc_2d else 'Lambertian, albedo %.2f' % self.surface_albedo))
+        rows.append(('phase function', 'Henyey-Greenstein' if self.sca is None else self.sca.pha.ID))
+        if (self.Nx > 1) or (self.Ny > 1):
+            rows.append(('domain', '%d x %d columns of %.2f km x %.2f km' % (self.Nx, self.Ny, self.dx / 1000.0, self.dy / 1000.0)))
+        rows.append(('photons', '%.1e per set (%s over %d g) x %d sets' % (self.photons_per_set, self.np_mode, self.Ng, self.Nrun)))
+        rows.append(('solver', 'in-process CUDA (sm_100a), device %d' % self.device))
+        width = max(len(k) for k, _ in rows)
+        print('Message [mcarats_ng]: run summary')
+        for k, v in rows:
+            print('    %s : %s' % (k.rjust(width), v))
 
 
 def cal_mca_azimuth(normal_azimuth_angle):

@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 102 /* 0.1.2: options.empty_runs (was reserved), options.smem_tally (was padding) */
+#define B200RT_VERSION 103 /* 0.1.3: scene.cer3d + (ref, ssa, asy) tables: (omega, apf) of the 3-D field derived on the GPU; Atm_abst3d
+                              supported; options.kernel; b200rt_run stream-asynchronous (one run in flight per handle) */
 
 /* error codes (0 = ok, negative = failure; message via b200rt_last_error) */
 enum {
@@ -99,7 +100,8 @@ typedef struct b200rt_scene {
     const float*  ext3d;          /* 1/m, see layout3d                                         */
     const float*  omg3d;
     const float*  apf3d;
-    const float*  abs3d;          /* [nz3][ny][nx] absorption perturbation 1/m, may be NULL    */
+    const float*  abs3d;          /* [nz3][ny][nx] Atm_abst3d: absorption coefficient added inside the 3-D block, 1/m,
+                                     >= 0 (treated as one more component with omega = 0); may be NULL            */
     /* tabulated phase functions, mca_sca.py:82-95 */
     int32_t npf, nang;            /* Sca_npf, Sca_nangi (npf == 0: none)                       */
     const double* ang;            /* [nang] scattering angle, degrees, increasing from 0 to 180 */
@@ -116,6 +118,16 @@ typedef struct b200rt_scene {
     int32_t nrad;                 /* Rad_nrad                                                  */
     int32_t _pad1;
     const b200rt_sensor* sensors; /* [nrad] host pointer                                       */
+    /* Optional: let the library derive (omega, apf) of the (single) 3-D component from the droplet effective radius,
+     * exactly as mca_atm_3d does on the host (er3t/rtm/mca/mca_atm.py:291-303): voxels with ext > 0 get
+     * omega = interp(ssa_tab)(cer), apf = interp(asy_tab)(cer) (linear, linearly extrapolated: Henyey-Greenstein with
+     * the Mie asymmetry parameter); clear voxels get omega = 1, apf = -1.  omg3d / apf3d are ignored (may be NULL). */
+    const float*  cer3d;          /* same layout as ext3d (np3d must be 1), um; NULL = use omg3d / apf3d */
+    int32_t nref;                 /* entries of the three tables (>= 2)                          */
+    int32_t _pad2;
+    const double* ref_tab;        /* [nref] effective radius, strictly increasing; host pointer  */
+    const double* ssa_tab;        /* [nref] single-scattering albedo                             */
+    const double* asy_tab;        /* [nref] asymmetry parameter                                  */
 } b200rt_scene;
 
 /* One (run, g) job = one MCARaTS invocation of the reference (mca_run.py:110-113). */
@@ -142,13 +154,17 @@ typedef struct b200rt_options {
     int32_t event_min;            /* lanes parked at an event that end a flight phase early; 0 = auto */
     int32_t empty_runs;           /* vertical merging of empty coarse cells into one box: 0 = auto (on when the 3-D
                                      layers are equally thick and no per-level tally is asked for), -1 = off        */
-    int32_t pool_slots;           /* photon slots per warp in shared memory: 32, 64, 80, 96, 128; 0 = auto (96) */
+    int32_t pool_slots;           /* photon slots in shared memory: per block 1024, 1536, 2048 (kernel 9) or per warp 32, 64,
+                                     80, 96, 128 (kernel 8); 0 = auto */
     int32_t iso_ss;               /* Pho_iso_SS: partial-3D switches to 1-D after this order   */
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */
     int32_t threads_per_block;    /* 0 = auto                                                  */
     int32_t blocks_per_sm;        /* 0 = auto                                                  */
     int32_t smem_tally;           /* block-private flux / heating tallies in shared memory when the whole tally is small
                                      (<= 2048 doubles): 0 = auto (on), -1 = off (global atomics only)               */
+    int32_t kernel;               /* transport kernel: 0 = auto, 9 = role-specialised warps + block-level photon pool
+                                     (pool_slots 1024 / 1536 / 2048), 8 = every warp runs every phase on its own pool   */
+    int32_t _reserved;
     double  wmin;                 /* Pho_wmin: Russian roulette threshold (0 = no roulette)    */
     double  wfac;                 /* Pho_wfac: weight given to roulette survivors              */
 } b200rt_options;
@@ -182,8 +198,10 @@ const char*  b200rt_last_error(void* handle);
  * tables. May be called again to replace the scene. */
 int          b200rt_upload_scene(void* handle, const b200rt_scene* scene, const b200rt_options* opt);
 
-/* Trace all jobs (asynchronously on `cuda_stream`, a cudaStream_t or NULL for the default stream;
- * tallies are zeroed first unless `accumulate` != 0). */
+/* Trace all jobs asynchronously on `cuda_stream` (a cudaStream_t or NULL for the default stream): the per-job tables are
+ * staged in page-locked memory and uploaded with cudaMemcpyAsync on that stream, nothing in the call waits for the GPU.
+ * Tallies are zeroed first unless `accumulate` != 0.  ONE run may be in flight per handle: a second b200rt_run,
+ * b200rt_upload_scene or b200rt_read_* first waits for the stream of the run in flight. */
 int          b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, void* cuda_stream);
 
 /* Wait for the stream of the last run; checks tallies for NaN/Inf. */

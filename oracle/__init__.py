@@ -3,10 +3,11 @@ oracle/ -- TEST INFRASTRUCTURE ONLY (never imported by er3t_b200/).
 
 * oracle_mc.cpp      fp64 CPU Monte Carlo restatement of the photon-transport path (PARITY UNPINNED
                      against MCARaTS, see the header of that file and DESIGN.md).
-* adding_doubling.py deterministic plane-parallel solver that pins oracle_mc.
+* adding_doubling.py deterministic plane-parallel solver (adding-doubling; tabulated phase functions, oblique views by
+                     azimuthal Fourier modes) that pins oracle_mc AND, through tests/golden/ad_fixtures.npz, the CUDA path.
 * philox_np.py       numpy Philox4x32-10 checked against the Random123 known-answer vectors.
-* host_ref.py        numpy restatements of the reference's host-side arithmetic
-                     (distribute_photon, cal_mca_azimuth, output weighting ...), pinned by tests/golden/.
+(The reference's host-side arithmetic -- distribute_photon, cal_mca_azimuth, output weighting ... -- needs no restatement
+here: tests/golden/make_golden.py runs the reference's own functions and commits their outputs.)
 
 Only tests/, __graft_entry__.smoke() and the cpu_baseline / `--impl reference` legs of bench.py may import this.
 """
@@ -24,7 +25,8 @@ _LIB = None
 
 def build(force=False):
     """Compile oracle_mc.cpp with the committed Makefile (g++ only)."""
-    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, 'oracle_mc.cpp')):
+    deps = [os.path.join(_HERE, 'oracle_mc.cpp'), os.path.join(_HERE, '..', 'include', 'b200rt.h')]      # the ABI structs are shared
+    if force or not os.path.isfile(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(d) for d in deps if os.path.isfile(d)):
         subprocess.check_call(['make', '-C', _HERE, '-s'] + (['-B'] if force else []))
     return _SO
 

@@ -13,6 +13,25 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a host without a GPU skips the `gpu` tests instead of erroring in their fixture.
+    On the B200 box (or with REQUIRE_GPU=1) nothing is skipped: a missing library or device is a hard failure there."""
+    import os
+    if os.environ.get('REQUIRE_GPU') == '1':
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason='no CUDA device on this host (the product path has no CPU fallback); set REQUIRE_GPU=1 to fail instead')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope='session')
 def solver():
     """One CUDA solver handle for the whole GPU session; fails loudly when the library or GPU is missing."""

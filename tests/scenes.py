@@ -146,3 +146,39 @@ def mean_sem(a):
     """mean and standard error over axis 0 (independent repetitions)."""
     a = np.asarray(a)
     return a.mean(axis=0), a.std(axis=0, ddof=1) / np.sqrt(a.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# deterministic plane-parallel benchmark cases (tests/golden/ad_fixtures.npz, made by tests/golden/make_ad_fixtures.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def ad_fixture(name):
+    """dict of the arrays of one adding-doubling benchmark case ('mie' or 'hg')."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ad_fixtures.npz'))
+    pre = name + '_'
+    return {k[len(pre):]: f[k] for k in f.files if k.startswith(pre)}
+
+
+def ad_scene(fx, hom3d=False, src_phi=200.0):
+    """The benchmark case as a transport scene.  View k of the fixture is (vza, dphi) with dphi = azimuth of the photon's
+    direction of travel toward the sensor minus the azimuth of the solar direction of travel; the sensor's VIEWING vector
+    (include/b200rt.h: `the`, `phi`) points the other way, hence phi_view = src_phi + dphi - 180.
+    hom3d: the cloud layer as a horizontally uniform 2 x 2-column 3-D block instead of a 1-D component (the
+    cld_gen_hom variant of config 1, er3t/rtm/mca/util.py:340-364)."""
+    z = fx['z']
+    sensors = [dict(the=180.0 - float(v), phi=(src_phi + float(d) - 180.0) % 360.0, nxr=1, nyr=1) for v, d in fx['views']]
+    kw = {}
+    if 'ang' in fx:
+        kw.update(ang=fx['ang'], pha=fx['pha'])
+    ext, omg, apf = fx['ext'].copy(), fx['omg'].copy(), fx['apf'].copy()
+    if hom3d:
+        icl = int(np.argmax(ext[1]))
+        e3 = np.full((2, 2, 1), ext[1, icl], dtype=np.float32)
+        o3 = np.full((2, 2, 1), omg[1, icl], dtype=np.float32)
+        a3 = np.full((2, 2, 1), apf[1, icl], dtype=np.float32)
+        for s in sensors:
+            s.update(nxr=2, nyr=2)
+        kw.update(nx=2, ny=2, dx=100.0, dy=100.0, iz3l=icl + 1, ext3d=e3, omg3d=o3, apf3d=a3)
+        ext, omg, apf = ext[:1], omg[:1], apf[:1]
+    return abi.HostScene(z, ext, omg, apf, sfc_type=1, sfc_param=(float(fx['albedo']), 0, 0, 0, 0), src_the=180.0 - float(fx['sza']),
+                         src_phi=src_phi, src_qmax=0.0, sensors=sensors, **kw)

@@ -30,7 +30,7 @@ def test_library_exports_every_symbol():
     for name in abi.EXPORTS:
         assert hasattr(lib, name), name
     lib.b200rt_version.restype = C.c_int
-    assert lib.b200rt_version() == 102
+    assert lib.b200rt_version() == 103
 
 
 def test_struct_layout_matches_header(tmp_path):

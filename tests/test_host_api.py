@@ -133,3 +133,38 @@ def test_all_sky_camera_through_the_public_api(inputs, tmp_path):
     # without the override the reference's fixed 500 x 500 grid is what the namelist carries
     m2 = run(inputs, tmp_path, sensor_type='all-sky camera', sensor_zenith_angle=180.0, sensor_altitude=0.0, dry_run=True)
     assert m2.nml[0]['Rad_nxr'] == 500 and m2.nml[0]['Rad_nyr'] == 500
+
+
+def test_hdf5_dump_matches_the_reference_call_for_call(monkeypatch, tmp_path):
+    """h5py is absent from the image, so the HDF5 branch of mca_out_ng.dump / load is exercised against a recording
+    stand-in (tests/fake_h5py.py).  The expected log was recorded from the REFERENCE's own dump (mca_out.py:209-233) by
+    tests/golden/make_h5_golden.py: same group, same dataset options (gzip 9, chunked), same attributes and types."""
+    import json
+    import os
+    import sys
+    import fake_h5py
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_h5_golden import sample_data
+    from er3t_b200.rtm.mca.mca_out import mca_out_ng
+    monkeypatch.setitem(sys.modules, 'h5py', fake_h5py)
+
+    class _M:
+        target = 'radiance'
+
+    o = object.__new__(mca_out_ng)
+    o.data, o.fname, o.mode, o.quiet, o.verbose, o.mca = sample_data(), str(tmp_path / 'out.h5'), 'mean', True, False, _M()
+    fake_h5py.reset()
+    o.dump()
+    want = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'h5_dump_calls.json')))
+    got = json.loads(json.dumps(fake_h5py.LOG))
+    assert got == want
+    # and the reader gets the same dictionary back (HDF5 branch of load: the file does not start with the zip magic)
+    with open(o.fname, 'wb') as f:
+        f.write(b'\x89HDF\r\n\x1a\n')
+    fake_h5py.FILES[o.fname] = fake_h5py.FILES.pop(o.fname) if o.fname in fake_h5py.FILES else None
+    r = object.__new__(mca_out_ng)
+    r.fname, r.mode, r.quiet, r.verbose = o.fname, 'mean', True, False
+    r.load()
+    for key, item in o.data.items():
+        assert np.array_equal(np.asarray(r.data[key]['data']), np.asarray(item['data']))
+        assert r.data[key]['name'] == item['name'] and r.data[key]['units'] == item['units']

@@ -235,3 +235,63 @@ def test_all_sky_camera_matches_parallel_projection_sensors():
         assert abs(m_c / m_p - 1.0) < 0.08 or abs(m_c - m_p) < 3.5 * np.hypot(s_c, s_p), (t, m_c, m_p, s_c, s_p)
     # the sun is seen at zenith angle 35 deg, azimuth 90 deg: that half of the sky is the brighter one
     assert cam.mean(axis=0)[V > 0].mean() > 1.3 * cam.mean(axis=0)[V < 0].mean()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tabulated (Mie) phase functions and oblique views against the deterministic solver
+# ---------------------------------------------------------------------------------------------------------------------
+def test_beam_source_solver_matches_node_beam_solver():
+    """Two independent formulations of the deterministic solver (solar beam as a quadrature node vs as a source term,
+    Radau vs Gauss grid) agree on fluxes and oblique radiances."""
+    ns = 40
+    mu, w = ad.radau_nodes(ns)
+    k0 = int(np.argmin(abs(mu - 0.85)))
+    z = scenes.std_z()
+    nz = z.size - 1
+    e0 = scenes.rayleigh_ext(z)
+    pr, ph = ad.rayleigh(), ad.hg(0.8)
+    layers = [dict(dz=1000.0, comps=[(e0[iz], 1.0, pr), (8e-3 if iz == 1 else 0.0, 0.99, ph)], absorb=2e-5 if iz < 5 else 0.0) for iz in range(nz - 1, -1, -1)]
+    views = [(0.0, 0.0), (30.0, 40.0), (60.0, 150.0)]
+    a = ad.solve_views(layers, 0.2, k0, nstream=ns, views=views, nmode=12)
+    b = ad.solve_beam(layers, 0.2, np.rad2deg(np.arccos(mu[k0])), nstream=ns, views=views, nmode=12)
+    assert np.max(np.abs(a['f_up'] - b['f_up'])) < 2e-6
+    assert np.max(np.abs(a['f_down'] - b['f_down'])) < 2e-6
+    assert np.allclose(a['rad_views'], b['rad_views'], rtol=3e-6)
+    assert abs(a['rad_views'][0] / ad.solve(layers, 0.2, k0, nstream=ns)['rad_nadir_toa'] - 1.0) < 1e-6   # (different azimuth quadratures)
+
+
+def test_fixture_hg_reproduced_at_low_resolution():
+    """The committed fixture is what oracle/adding_doubling.py produces (HG converges with few streams)."""
+    fx = scenes.ad_fixture('hg')
+    z = fx['z']; nz = z.size - 1
+    pr, ph = ad.rayleigh(), ad.hg(0.85)
+    layers = [dict(dz=float(z[iz + 1] - z[iz]), comps=[(fx['ext'][0, iz], 1.0, pr), (fx['ext'][1, iz], fx['omg'][1, iz], ph)], absorb=fx['absg'][iz])
+              for iz in range(nz - 1, -1, -1)]
+    r = ad.solve_beam(layers, float(fx['albedo']), float(fx['sza']), nstream=48, views=[tuple(v) for v in fx['views']], nmode=16)
+    assert np.max(np.abs(r['f_up'] - fx['f_up'])) < 2e-5
+    assert np.max(np.abs(r['f_down'] - fx['f_down'])) < 2e-5
+    assert np.allclose(r['rad_views'], fx['rad_views'], rtol=2e-4)
+
+
+@pytest.mark.parametrize('name', ['mie', 'hg'])
+def test_oracle_against_deterministic_oblique_views_and_tables(name):
+    """oracle_mc.cpp against the converged adding-doubling result: flux at all 21 levels, TOA radiance at nadir and four
+    oblique directions, for the 498-angle Mie table (piecewise linear in mu) and for Henyey-Greenstein."""
+    fx = scenes.ad_fixture(name)
+    sc = scenes.ad_scene(fx)
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(250000, nslab, abs1d=fx['absg'])
+    r = oracle.run(sc, opt, jobs)
+    mu0 = float(fx['mu0'])
+    f = r['flux'][:, :, :, 0, 0]                                   # (nslab, 3, nlev)
+    for var, key in ((2, 'f_up'), (1, 'f_down'), (0, 'f_down_direct')):
+        m, s = scenes.mean_sem(f[:, var])
+        # 2e6 photons: standard error of a flux ~ 4e-4 * mu0
+        assert np.max(np.abs(m - fx[key]) / (4.0 * s + 2e-4 * mu0)) < 1.0, (key, np.max(np.abs(m - fx[key])) / mu0)
+    rad = r['rad'].reshape(nslab, -1)
+    m, s = scenes.mean_sem(rad)
+    z = (m - fx['rad_views']) / np.sqrt(s ** 2 + (3e-4 * fx['rad_views']) ** 2)
+    assert np.max(np.abs(z)) < 4.0, (z, m / fx['rad_views'])
+    assert np.max(np.abs(m / fx['rad_views'] - 1.0)) < 0.03        # and in absolute terms: a few per cent at 2e6 photons
+    assert abs(energy_balance(r['stats'])) < 1e-10
