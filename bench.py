@@ -9,8 +9,12 @@ bench.py -- headline benchmark of the photon-transport path: photons/s on the 3-
 
 One "step" = one complete `mcarats_ng` job set (Nrun x Ng jobs = 3 x 1e8 photons) over the synthetic scene.
 `value`  : photons/s with the scene already resident in HBM (b200rt_run only; CUDA events on the launching stream).
-`e2e`    : photons/s through the public API (mcarats_ng + mca_out_ng) with HOST numpy inputs: scene packing, H2D,
-           transport, D2H and the run statistics are all inside the timed region.
+`e2e`    : photons/s through the public API, starting from the RAW cloud fields (extinction, effective radius) as host
+           numpy arrays: mca_atm_3d(device_props=True) + mcarats_ng + mca_out_ng -- the input builder, scene packing
+           (omega / apf derived on the GPU), H2D, transport, D2H and the run statistics are all inside the timed region.
+`strong` : the FIXED 3e8-photon job set sharded over the N ranks (N > 1 only; `value` stays weak-scaled).
+`accuracy`: error of the GPU path against the deterministic adding-doubling fixture (plane-parallel Mie cloud) and
+           against the CPU oracle on a scaled copy of this workload.
 Inputs are larger than L2 (3-D fields 370 MB in HBM vs 126 MB L2), so no explicit L2 flush between iterations.
 Rank 0 prints ONE JSON line.
 """
@@ -31,12 +35,13 @@ sys.path.insert(0, ROOT)
 SEED = 20260101
 
 
-def build_workload(nx=480, ny=480, nz3=100, photons=1e8, nrun=3):
-    """BASELINE.json configs[1] as synthetic input (SURVEY.md 8d 'C2', workloads.c2): kwargs for mcarats_ng + abs object."""
+def build_workload(nx=480, ny=480, nz3=100, photons=1e8, nrun=3, parts=False):
+    """BASELINE.json configs[1] as synthetic input (SURVEY.md 8d 'C2', workloads.c2): kwargs for mcarats_ng + abs object
+    (+ the raw cloud / atmosphere / phase objects the e2e leg rebuilds mca_atm_3d from, with parts=True)."""
     import workloads
-    kw, abs0 = workloads.c2(scale=1.0, photons=photons, nx=nx, ny=ny, nz3=nz3, nrun=nrun)
-    kw['fdir'] = 'tmp-data/bench'
-    return kw, abs0
+    out = workloads.c2(scale=1.0, photons=photons, nx=nx, ny=ny, nz3=nz3, nrun=nrun, parts=parts)
+    out[0]['fdir'] = 'tmp-data/bench'
+    return out
 
 
 class ClockSampler:
@@ -143,6 +148,66 @@ def cpu_oracle_rate(kw, abs0, seconds=15.0, nthreads=0):
         nphot = int(max(nphot * 2, min(5e7, rate * (seconds - total_t) * 0.8)))
 
 
+# the only throughput the reference publishes (docs/source/other/contest.rst:15-24): 3e8 photons in <= 45 s on
+# 24 CPUs for a 480 x 480 x 4 scene -- a derived lower bound on another scene, quoted for context only
+PUBLISHED = {'value': 6.7e6, 'unit': 'photons/s', 'cores': 24, 'what': 'MCARaTS, derived lower bound, 480x480x4 scene (contest.rst:15-24)'}
+
+
+def accuracy_summary(sol):
+    """Error of the CUDA path (a) against the converged deterministic solution of the plane-parallel Mie-cloud case
+    (tests/golden/ad_fixtures.npz, oracle/adding_doubling.py) at 4e8 photons, (b) against the CPU oracle on a scaled
+    copy of the bench workload (per-pixel z-scores, domain-mean radiance)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import scenes
+    import oracle
+    import workloads
+    from er3t_b200 import abi
+    from er3t_b200.rtm.mca import mcarats_ng
+    out = {}
+    # (a) deterministic
+    fx = scenes.ad_fixture('mie')
+    nslab = 8
+    sc = scenes.ad_scene(fx)
+    opt = abi.make_options(target=abi.TARGET_FLUX | abi.TARGET_RADIANCE, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(50000000, nslab, abs1d=fx['absg'])
+    sol.upload_scene(sc, opt)
+    sol.run(jobs)
+    r = sol.results()
+    nlev = fx['z'].size
+    flux = r['flux'].reshape(nslab, 3, nlev)
+    rad = r['rad'].reshape(nslab, -1)
+    mu0 = float(fx['mu0'])
+    fm = flux.mean(axis=0)
+    rm, rs = rad.mean(axis=0), rad.std(axis=0, ddof=1) / np.sqrt(nslab)
+    out['vs_adding_doubling'] = {
+        'case': 'config-1 atmosphere, tau = 10 cloud with the 498-angle Mie table, SZA 30, 4e8 photons',
+        'flux_up_max_rel_err': float(np.max(np.abs(fm[2] - fx['f_up']) / np.maximum(fx['f_up'], 0.05 * mu0))),
+        'flux_down_max_rel_err': float(np.max(np.abs(fm[1] - fx['f_down']) / np.maximum(fx['f_down'], 0.05 * mu0))),
+        'radiance_rel_err': [float(v) for v in (rm / fx['rad_views'] - 1.0)],
+        'radiance_rel_sem': [float(v) for v in (rs / fx['rad_views'])],
+        'views_vza_dphi': fx['views'].tolist()}
+    # (b) oracle on a scaled copy of the workload (north_star: domain mean within 0.5 %, pixels within 3 combined sigma)
+    kws, _ = workloads.c2(scale=0.004, photons=1e8)
+    nrep = 6
+    m = mcarats_ng(**dict(kws, Nrun=nrep, dry_run=True))
+    ja = dict(m.jobs_args)
+    jobs, keep = abi.make_jobs(**ja)
+    sol.upload_scene(m.scene, m.options)
+    sol.run(jobs)
+    g = sol.results()['rad'].reshape(nrep, -1)
+    c = oracle.run(m.scene, m.options, jobs, nthreads=host_cores())['rad'].reshape(nrep, -1)
+    gm, cm = g.mean(axis=0), c.mean(axis=0)
+    se = np.sqrt(g.var(axis=0, ddof=1) / nrep + c.var(axis=0, ddof=1) / nrep)
+    ok = se > 0
+    z = (gm[ok] - cm[ok]) / se[ok]
+    out['vs_oracle_c2_scaled'] = {
+        'case': '%d x %d x %d voxels, %d photons x %d runs (workloads.c2 scale 0.004)' % (m.scene.struct.nx, m.scene.struct.ny, m.scene.struct.nz3,
+                                                                                            int(np.sum(ja['nphot']) / nrep), nrep),
+        'domain_mean_rel_err': float(gm.mean() / cm.mean() - 1.0), 'pixel_z_rms': float(np.sqrt(np.mean(z ** 2))),
+        'pixel_z_max_abs': float(np.max(np.abs(z))), 'pixels_beyond_3_sigma_frac': float(np.mean(np.abs(z) > 3.0))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -154,6 +219,7 @@ def main():
     ap.add_argument('--nz3', type=int, default=100)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-accuracy', action='store_true')
     ap.add_argument('--sv', type=str, default='0,0,0')
     ap.add_argument('--empty-runs', type=int, default=0, help='A/B switch of the resident leg: -1 = no vertical merging of empty coarse cells')
     args = ap.parse_args()
@@ -192,7 +258,7 @@ def main():
         line = {'impl': 'reference', 'metric': 'photons/s', 'value': val, 'unit': 'photons/s', 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f64', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': val, 'unit': 'photons/s', 'cores': cores, 'kind': 'port',
+                'cpu_baseline': {'value': val, 'unit': 'photons/s', 'cores': cores, 'kind': 'port', 'published_reference': PUBLISHED,
                                  'sample': '%d photons per step of the same scene (1 run x 16 g), oracle/oracle_mc.cpp with OpenMP; MCARaTS itself cannot be built offline' % sample},
                 'e2e': {'value': val, 'unit': 'photons/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
@@ -209,7 +275,7 @@ def main():
     rank, world, local = edist.init_from_env()
     torch.cuda.set_device(local)
     # weak scaling: every GPU traces the full BASELINE photon count, the job set grows with the number of GPUs
-    kw, abs0 = build_workload(args.nx, args.nx, args.nz3, args.photons * world)
+    kw, abs0, parts = build_workload(args.nx, args.nx, args.nz3, args.photons * world, parts=True)
     kw['device'] = local
     kw['supervoxel'] = tuple(int(v) for v in args.sv.split(','))
     kw['shard'] = (rank, world)
@@ -258,12 +324,47 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
     value = photons_step * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public API (host inputs, H2D and D2H inside the timed region)
+    # ---- strong scaling (N > 1): the FIXED BASELINE job set (3 x 1e8 photons) sharded over the ranks, same timing rules
+    strong = None
+    if world > 1:
+        kws = dict(kw, photons=args.photons)
+        preps = mcarats_ng(**dict(kws, dry_run=True))
+        jobs_s, keep_s = abi.make_jobs(**preps.jobs_args)
+        sol.upload_scene(preps.scene, preps.options)
+
+        def step_strong():
+            sol.run(jobs_s, sync=False)
+            return edist.allreduce_results(sol, to_host=False)
+        for _ in range(args.warmup):
+            step_strong()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_strong()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_s = float(t.item())
+        sol.sync()
+        nphot_s = int(np.sum(preps.jobs_args['nphot']))
+        strong = {'value': nphot_s * args.steps / (ms_s * 1e-3), 'unit': 'photons/s', 'photons_per_step': nphot_s, 'ms_per_step': ms_s / args.steps,
+                  'kernel_ms_per_launch_rank0': float(sol.stats()['elapsed_ms']),
+                  'efficiency_vs_weak': (nphot_s * args.steps / (ms_s * 1e-3)) / value,
+                  'note': 'same job set as N = 1 (3 x 1e8 photons), photons of every job split over the ranks, one in-place NCCL all-reduce of the tallies per step'}
+
+    # ---- end to end through the public API (host inputs, H2D and D2H inside the timed region).  The step starts from the
+    #      raw cloud fields: mca_atm_3d(device_props=True) hands extinction + effective radius to the library, whose
+    #      packing kernel derives (omega, apf) on the GPU (er3t/rtm/mca/mca_atm.py:231-337 is the host loop it replaces)
     e2e = None
     esteps = max(1, args.e2e_steps)
     h2d = d2h = 0
+    from er3t_b200.rtm.mca import mca_atm_3d
+
     def step_e2e():
-        m = mcarats_ng(**dict(kw, solver_obj=sol, reduce=(lambda s: edist.allreduce_results(s)) if world > 1 else None))
+        a3 = mca_atm_3d(cld_obj=parts['cld'], atm_obj=parts['atm'], pha_obj=parts['pha'], quiet=True, device_props=True)
+        m = mcarats_ng(**dict(kw, atm_3ds=[a3], solver_obj=sol, reduce=(lambda s: edist.allreduce_results(s)) if world > 1 else None))
         out = mca_out_ng(mca_obj=m, abs_obj=abs0, mode='mean', squeeze=True)
         return m, out
     step_e2e()
@@ -281,7 +382,13 @@ def main():
     d2h = int(8 * prep.scene.rad_size(prep.nslab))
     e2e = {'value': photons_step * esteps / dt, 'unit': 'photons/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'steps': esteps, 'ms_per_step': 1e3 * dt / esteps,
-           'api': 'er3t_b200.rtm.mca.mcarats_ng(...) + mca_out_ng(...) with host numpy inputs (3-D fields page-locked by mca_atm_3d)'}
+           'api': 'er3t_b200.rtm.mca: mca_atm_3d(cld, atm, pha, device_props=True) + mcarats_ng(...) + mca_out_ng(...) from host numpy '
+                  'extinction / effective-radius fields: the input builder is INSIDE the timed region'}
+
+    # ---- accuracy (rank 0, N = 1): the number the metric is quoted with ("photons/s ...; flux/radiance err")
+    accuracy = None
+    if world == 1 and not args.no_accuracy:
+        accuracy = accuracy_summary(sol)
 
     if world > 1:
         torch.distributed.barrier()
@@ -291,21 +398,32 @@ def main():
     peak, peak_src = measured_peak()
     t_kernel = float(np.mean(kern_ms)) * 1e-3
     achieved = float(np.mean(bytes_alg)) / t_kernel / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'transport_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+    cap = ncu_traffic('ncu_capture') or {}
+    wipp = cap.get('warp_instructions_per_photon')
+    sm_hz = 1e6 * float((clocks or {}).get('sm_mhz') or 1965.0)
+    issue = None
+    if wipp:
+        # issue-slot roofline: warp instructions per photon (ncu) x photons/s of the kernel / (148 SMs x 4 schedulers x SM clock)
+        ach = wipp * (photons_step / world) / t_kernel
+        issue = {'achieved': ach, 'peak': 148 * 4 * sm_hz, 'unit': 'warp instructions/s', 'frac': ach / (148 * 4 * sm_hz),
+                 'warp_instructions_per_photon': wipp, 'source': cap.get('file')}
+    roofline = {'bound': 'hbm', 'limiter': 'instruction issue / dependent-gather latency (the HBM fraction only says that bytes are not the limit)',
+                'issue': issue,
+                'kernel': 'transport_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': ncu_traffic(), 'peak_source': peak_src, 'bytes_alg_per_launch': float(np.mean(bytes_alg)),
                 'kernel_ms_per_launch': float(np.mean(kern_ms)),
                 'bytes_alg_per_photon': float(np.mean(bytes_alg)) / (photons_step / world),
-                'ncu': ncu_traffic('ncu_capture')}
+                'ncu': cap}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r, n, cores = cpu_oracle_rate(kw, abs0, seconds=15.0)
-        cpu = {'value': r, 'unit': 'photons/s', 'cores': cores, 'kind': 'port',
+        cpu = {'value': r, 'unit': 'photons/s', 'cores': cores, 'kind': 'port', 'published_reference': PUBLISHED,
                'sample': '%d photons of the same scene (1 run x 16 g) on the host cores, oracle/oracle_mc.cpp (fp64, exact traversal, OpenMP)' % n}
     line = {'metric': 'photons/s', 'value': value, 'unit': 'photons/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (fp64 tallies)', 'data': 'synthetic', 'config': config,
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-            'photons_per_step': photons_step}
+            'photons_per_step': photons_step, 'accuracy': accuracy, 'strong': strong}
     print(json.dumps(line))
 
 

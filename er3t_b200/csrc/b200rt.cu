@@ -97,6 +97,7 @@ struct DevScene {
     // small flux / heating tallies (plane-parallel and few-column scenes) are kept per block in shared memory and flushed
     // once: all photons would otherwise hammer the same few L2 addresses
     int ntal_flux_smem, ntal_heat_smem;   // doubles of the whole flux / heating tally held in shared memory (0: global atomics)
+    int tal_per_warp;         // 1: every warp of a block keeps its own copy (very small tallies), 0: one copy per block
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
     const float* e1tot;       // [nz]
@@ -345,8 +346,9 @@ struct Smem {
     const int4* grpB;     // [ngroup]    (first fine slab, one-past-last fine slab, first layer, one-past-last layer)
     double* acc;          // energy sums [4][32]: toa, sfc, (unused), roulette; one slot per lane and block
     double* acc_atm;      // atmospheric absorption: one slot per thread
-    double* ftal;         // block-private flux tally (same layout as the global one) or nullptr
-    double* htal;         // block-private heating tally or nullptr
+    double* ftal;         // block- or warp-private flux tally (same layout as the global one) or nullptr
+    double* htal;         // block- or warp-private heating tally or nullptr
+    int tal_mode;         // 1: one copy per block (shared atomics); 2: one copy per warp (plain read-modify-write)
     unsigned* cnt;        // event counters [8][32]: one slot per lane and block (flushed to 64-bit totals per block)
 };
 enum { ACC_TOA = 0, ACC_SFC = 1, ACC_ATM = 2, ACC_RR = 3 };
@@ -501,39 +503,66 @@ __device__ __forceinline__ void tally_add_shared(double* p, double v) {
     asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// column of the atmosphere grid a tally goes to
-__device__ __forceinline__ void tally_col(const DevScene& S, const Photon& p, int& fx, int& fy) {
-    if (p.flags & FL_FROZEN) { fx = p.cix; fy = p.ciy; }
-    else {
-        fx = min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
-        fy = min(S.ny - 1, max(0, int(p.y * S.inv_dy)));
+// ---- tallies -------------------------------------------------------------------------------------------------------
+// Warp-aggregated add: lanes of the (currently converged) warp that target the SAME address are summed first
+// (__match_any_sync, then every group walks its own member list with shuffles) and ONE lane per address performs the
+// update.  Plane-parallel and few-column scenes send most of a warp to the same few addresses (all lanes of a freshly
+// regenerated batch cross the same level; every local estimate of a 1 x 1-pixel sensor hits one pixel): without this a
+// shared-memory fp64 add (a CAS loop) or an L2 reduction serialises 32 ways.
+//   mode 0: global atomic; mode 1: shared-memory atomic (block-private tally); mode 2: plain read-modify-write
+//   (warp-private tally: no other warp touches it and, after aggregation, no two lanes of this warp do)
+__device__ __forceinline__ void tally_agg(double* p, double v, int mode) {
+    const unsigned am = __activemask();
+    const unsigned grp = __match_any_sync(am, reinterpret_cast<unsigned long long>(p));
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(grp) - 1;
+    double s = v;
+    if (grp & (grp - 1)) {                        // more than one lane on this address
+        s = 0.0;
+        for (unsigned r = grp; r; r &= r - 1) s += __shfl_sync(grp, v, __ffs(r) - 1);
+    }
+    if (lane == leader) {
+        if (mode == 2) *p += s;
+        else if (mode == 1) tally_add_shared(p, s);
+        else tally_add(p, s);
     }
 }
 
-// The out-of-line part of a flux / heating tally gets everything by value (the caller reads the scene from the constant
-// bank; a by-reference DevScene would turn every field into a dependent generic load): two independent loads (the
-// complete per-level scale, the slab offset of the job), one fp64 multiply, one atomic.
-__device__ __noinline__ void tally_at(double* base, int is_shared, const double* scale, const unsigned long long* slab_off,
-                                      unsigned long long rel, double w) {
-    const double v = w * __ldg(scale);
-    const size_t idx = size_t(__ldg(slab_off) + rel);
-    if (is_shared) tally_add_shared(base + idx, v);
-    else tally_add(base + idx, v);
+// Everything a flux / heating tally of one photon needs beyond (variable, level, column, weight); loaded once per phase
+// visit instead of once per tally.
+struct TallyCtx {
+    const double* fs;             // complete per-level scale of the photon's job: norm x columns x caller's factor
+    unsigned long long foff, hoff;   // start of the job's slab in the flux / heating tally
+};
+__device__ __forceinline__ TallyCtx tally_ctx(const DevScene& S, int job) {
+    TallyCtx t;
+    t.fs = S.job_fscale + size_t(job) * (S.nz + 1);
+    t.foff = S.jobs[job].flux_off;
+    t.hoff = S.jobs[job].heat_off;
+    return t;
 }
-__device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
-    int fx, fy;
-    tally_col(S, p, fx, fy);
-    tally_at(sm.ftal ? sm.ftal : S.flux, sm.ftal != nullptr, S.job_fscale + p.job * (S.nz + 1) + lev, &S.jobs[p.job].flux_off,
-             (unsigned long long)(var * (S.nz + 1) + lev) * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx),
-             double(p.w));
-    if (!sm.ftal) CNT_ADD(CNT_TALLY, 1u);          // counts updates that reach global memory; block-private ones are counted at the flush
+// column of the atmosphere grid from the horizontal position in units of fine cells (svx x svy columns each)
+__device__ __forceinline__ int tally_col_u(const DevScene& S, float ux, float uy) {
+    const int fx = min(S.nx - 1, max(0, __float2int_rd(ux * float(S.svx))));
+    const int fy = min(S.ny - 1, max(0, __float2int_rd(uy * float(S.svy))));
+    return fy * S.nx + fx;
 }
-__device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
-    int fx, fy;
-    tally_col(S, p, fx, fy);
-    tally_at(sm.htal ? sm.htal : S.heat, sm.htal != nullptr, S.job_fscale + p.job * (S.nz + 1) + iz, &S.jobs[p.job].heat_off,
-             (unsigned long long)iz * (unsigned long long)(S.nx * S.ny) + (unsigned long long)(fy * S.nx + fx), dep);
-    if (!sm.htal) CNT_ADD(CNT_TALLY, 1u);
+__device__ __forceinline__ int tally_col_m(const DevScene& S, const Photon& p) {
+    if (p.flags & FL_FROZEN) return p.ciy * S.nx + p.cix;
+    return min(S.ny - 1, max(0, int(p.y * S.inv_dy))) * S.nx + min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
+}
+// tal_mode: 0 global atomics, 1 block-private shared tally, 2 warp-private shared tally
+__device__ __forceinline__ void flux_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int var, int lev, int col, float w, unsigned& n_tal) {
+    const double v = double(w) * __ldg(t.fs + lev);
+    const size_t idx = size_t(t.foff) + size_t(var * (S.nz + 1) + lev) * size_t(S.nx * S.ny) + size_t(col);
+    if (sm.ftal) tally_agg(sm.ftal + idx, v, sm.tal_mode);
+    else { tally_add(S.flux + idx, v); ++n_tal; }
+}
+__device__ __forceinline__ void heat_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int iz, int col, double dep, unsigned& n_tal) {
+    const double v = dep * __ldg(t.fs + iz);
+    const size_t idx = size_t(t.hoff) + size_t(iz) * size_t(S.nx * S.ny) + size_t(col);
+    if (sm.htal) tally_agg(sm.htal + idx, v, sm.tal_mode);
+    else { tally_add(S.heat + idx, v); ++n_tal; }
 }
 
 // layer that contains z among layers [l0, l1)
@@ -1449,7 +1478,11 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         }
     }
 }
-#include "transport_v9.cuh"
+// The role-specialised variant (geometry warps / event warps, block-level pool, setmaxnreg) is an experiment that
+// measured SLOWER than this kernel on every config (profiles/README.md, r02_c); it is compiled only on request.
+#ifdef B200RT_WITH_V9
+#include "../../experiments/transport_v9.cuh"
+#endif
 #undef ACC_ADD
 #undef CNT_ADD
 
@@ -2151,7 +2184,10 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     int tpb = H->opt.threads_per_block > 0 ? H->opt.threads_per_block : RT_TPB;
     tpb = std::min(RT_TPB, std::max(32, (tpb / 32) * 32));
     const char* kenv = getenv("B200RT_KERNEL");
-    const int kver = kenv ? atoi(kenv) : (H->opt.kernel == 8 ? 8 : 9);
+    const int kver = kenv ? atoi(kenv) : (H->opt.kernel == 9 ? 9 : 8);
+#ifndef B200RT_WITH_V9
+    if (kver == 9) return fail(H, B200RT_ERR_ARG, "options.kernel = 9 (role-specialised experiment) is not part of this build (-DB200RT_WITH_V9)");
+#else
     if (kver == 9) {
         // role-specialised kernel: one block per SM, block-level photon pool (transport_v9.cuh)
         int npb = H->pool_slots >= 1024 ? H->pool_slots : V9_NPB;
@@ -2173,7 +2209,9 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
         kern<<<grid, V9_NT, smem, st>>>(S);
         CK(cudaGetLastError());
         CK(cudaEventRecord(H->ev1, st));
-    } else {
+    } else
+#endif
+    {
     const int np = H->pool_slots > 0 && H->pool_slots <= 128 ? H->pool_slots : 96;
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-__all__ = ['init_from_env', 'allreduce_results', 'shard_from_env']
+__all__ = ['init_from_env', 'allreduce_results', 'shard_from_env', 'tally_views']
 
 
 def shard_from_env():
@@ -32,32 +32,53 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+class _DeviceDoubles:
+    """Zero-copy view of `n` doubles at a device address for torch (`torch.as_tensor` honours __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+
+
+def tally_views(solver):
+    """torch tensors that ALIAS the library-owned tally buffers (b200rt_tally_ptrs): {'flux' | 'rad' | 'heat': tensor or None}."""
+    import torch
+    out = {}
+    for key, (ptr, n) in solver.tally_ptrs().items():
+        out[key] = torch.as_tensor(_DeviceDoubles(ptr, n), device='cuda:%d' % solver.device) if (ptr and n) else None
+    return out
+
+
 def allreduce_results(solver, to_host=True):
     """
-    Sum the tallies of all ranks.  With NCCL the library's device buffers are copied device-to-device into torch
-    tensors (b200rt_read_* accepts device destinations), reduced over NVLink, and only then brought to the host; with
-    gloo (CPU tests) the host arrays are reduced.  Event counters are reduced with the same collective.
+    Sum the tallies of all ranks.  With NCCL the all-reduce runs IN PLACE on the library's own device buffers (no staging
+    tensor, no device-to-device copy): afterwards every rank's handle holds the global tallies and `solver.results()` /
+    `b200rt_read_*` return them.  With gloo (CPU tests) the host arrays are reduced.  The run is waited for first
+    (`solver.sync()`: NaN guard + fresh event counters), and the event counters are reduced with the same collective.
     """
     import torch
     import torch.distributed as dist
     res = {'flux': None, 'rad': None, 'heat': None}
     world = dist.get_world_size() if dist.is_initialized() else 1
     use_cuda = world > 1 and dist.get_backend() == 'nccl'
-    ptrs = solver.tally_ptrs() if hasattr(solver, 'tally_ptrs') else None
-    readers = {'flux': getattr(solver, 'read_flux', None), 'rad': getattr(solver, 'read_rad', None), 'heat': getattr(solver, 'read_heat', None)}
-    host = solver.results() if not use_cuda else None
+    if hasattr(solver, 'sync'):
+        solver.sync()
     st = solver.stats()
-    for key in ('flux', 'rad', 'heat'):
-        if use_cuda:
-            n = ptrs[key][1]
-            if n == 0:
+    if use_cuda:
+        views = tally_views(solver)
+        for key in ('flux', 'rad', 'heat'):
+            t = views[key]
+            if t is None:
                 continue
-            t = torch.empty(n, dtype=torch.float64, device='cuda')
-            rc = solver.lib.b200rt_read_flux if key == 'flux' else (solver.lib.b200rt_read_rad if key == 'rad' else solver.lib.b200rt_read_heat)
-            solver._check(rc(solver.handle, t.data_ptr(), n), 'b200rt_read_' + key)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            res[key] = t.cpu().numpy() if to_host else t
-        else:
+            res[key] = t
+        if to_host:
+            torch.cuda.synchronize()
+            host = solver.results()
+            for key in ('flux', 'rad', 'heat'):
+                res[key] = host[key]
+    else:
+        host = solver.results()
+        for key in ('flux', 'rad', 'heat'):
             a = host[key]
             if a is None:
                 continue
@@ -72,7 +93,7 @@ def allreduce_results(solver, to_host=True):
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
         for k, x in zip(keys, v.cpu().tolist()):
             st[k] = type(st[k])(x)
-    if res['flux'] is not None and hasattr(solver, 'scene'):
-        res['flux'] = res['flux'].reshape(solver.scene.flux_shape(solver.options.nslab)) if not hasattr(res['flux'], 'is_cuda') else res['flux']
+    if res['flux'] is not None and hasattr(solver, 'scene') and not hasattr(res['flux'], 'is_cuda'):
+        res['flux'] = res['flux'].reshape(solver.scene.flux_shape(solver.options.nslab))
     res['stats'] = st
     return res

@@ -162,8 +162,9 @@ typedef struct b200rt_options {
     int32_t blocks_per_sm;        /* 0 = auto                                                  */
     int32_t smem_tally;           /* block-private flux / heating tallies in shared memory when the whole tally is small
                                      (<= 2048 doubles): 0 = auto (on), -1 = off (global atomics only)               */
-    int32_t kernel;               /* transport kernel: 0 = auto, 9 = role-specialised warps + block-level photon pool
-                                     (pool_slots 1024 / 1536 / 2048), 8 = every warp runs every phase on its own pool   */
+    int32_t kernel;               /* transport kernel: 0 = auto (8), 8 = every warp runs every phase on its own photon pool,
+                                     9 = experiment: role-specialised warps + block-level pool (only in builds made with
+                                     -DB200RT_WITH_V9; measured slower)                                 */
     int32_t _reserved;
     double  wmin;                 /* Pho_wmin: Russian roulette threshold (0 = no roulette)    */
     double  wfac;                 /* Pho_wfac: weight given to roulette survivors              */

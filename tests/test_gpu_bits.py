@@ -167,3 +167,35 @@ def test_public_api_on_gpu_matches_oracle_backed_run(solver, tmp_path):
     z = (gm - cm) / np.sqrt(gs ** 2 + cs ** 2)
     assert np.mean(np.abs(z) > 3.0) <= 0.05 and np.max(np.abs(z)) < 7.0
     assert abs(gm.mean() / cm.mean() - 1.0) < 0.01
+
+
+def test_device_derived_omega_apf_equal_host_interpolation(solver):
+    """mca_atm_3d(device_props=True): (omega, apf) of the cloudy voxels are derived from the effective radius by the
+    scene-packing kernel (scene.cer3d) instead of the host loop of er3t/rtm/mca/mca_atm.py:291-303.  Same float32 values
+    => the same photon histories => identical tallies and event counts, bit for bit up to the fp64 summation order."""
+    import datetime
+    import er3t_b200.pre as bpre
+    from er3t_b200.rtm import mca as bmca
+    atm0 = bpre.atm_atmmod(levels=np.linspace(0, 20, 21))
+    abs0 = bpre.abs_16g(wavelength=650.0, atm_obj=atm0)
+    cld0 = bpre.cld_gen_les(Nx=40, Ny=36, dx=0.1, dy=0.1, altitude=np.arange(1.25, 3.8, 0.5), seed=5, atm_obj=atm0)
+    # float32-representable radii: the GPU receives the field as float32 (include/b200rt.h)
+    cld0.lay['cer']['data'] = np.asarray(cld0.lay['cer']['data'], dtype=np.float32).astype(np.float64)
+    pha0 = bpre.pha_mie_wc(wavelength=650.0, reff=[4.0, 8.0, 12.0, 16.0, 20.0], nr=32)
+    out = []
+    for dev in (False, True):
+        a3 = bmca.mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True, device_props=dev)
+        m = bmca.mcarats_ng(date=datetime.datetime(2017, 8, 13), atm_1ds=[bmca.mca_atm_1d(atm_obj=atm0, abs_obj=abs0)], atm_3ds=[a3], Ng=16,
+                            target='radiance', surface_albedo=0.05, sca=bmca.mca_sca(pha_obj=pha0), solar_zenith_angle=30.0,
+                            solar_azimuth_angle=45.0, Nrun=2, weights=abs0.coef['weight']['data'], solver='3D', quiet=True, photons=4e5, seed=11,
+                            solver_obj=solver, iz3l_fix=True)
+        out.append((m, a3))
+    (m0, a0), (m1, a1) = out
+    assert m1.scene.cer3d is not None and m1.scene.omg3d is None            # the device path really was taken
+    for k in ('n_coll', 'n_tent', 'n_sfc', 'n_roulette_kill', 'photons', 'n_cell'):
+        assert m0.stats[k] == m1.stats[k], k
+    assert np.allclose(m0.fused['radiance'][0], m1.fused['radiance'][0], rtol=1e-10, atol=1e-16)
+    # and the lazily evaluated namelist payload of the device variant equals the host arrays
+    assert np.array_equal(np.asarray(a1.nml['Atm_omgp3d']['data']), a0.nml['Atm_omgp3d']['data'])
+    assert np.array_equal(np.asarray(a1.nml['Atm_apfp3d']['data']), a0.nml['Atm_apfp3d']['data'])
+    assert np.array_equal(np.asarray(a1.nml['Atm_tmpa3d']['data']), a0.nml['Atm_tmpa3d']['data'])

@@ -318,3 +318,37 @@ def test_3d_all_sky_camera(solver):
         a, b = gcam[(slice(None),) + sel].mean(axis=(1, 2)), ccam[(slice(None),) + sel].mean(axis=(1, 2))
         am, asem = scenes.mean_sem(a); bm, bsem = scenes.mean_sem(b)
         assert abs(am / bm - 1.0) < 0.03 or abs(am - bm) < 3.5 * np.hypot(asem, bsem), (am, bm, asem, bsem)
+
+
+def test_3d_absorption_field_abst3d(solver):
+    """Atm_abst3d != 0 (er3t/rtm/mca/mca_inp.py:232-235, mca_atm.py:249): the CUDA path treats the 3-D absorption field as one
+    more component with omega = 0 (absorption at collisions), the oracle integrates it along the path -- same expectation."""
+    sc0 = scenes.scene_3d()
+    rng = np.random.default_rng(11)
+    a3 = (3.0e-4 * rng.random((16, 12, 4))).astype(np.float32)
+    a3[rng.random((16, 12, 4)) < 0.4] = 0.0
+    sc = abi.HostScene(sc0.zgrd, sc0.ext1d, sc0.omg1d, sc0.apf1d, nx=16, ny=12, dx=100.0, dy=100.0, iz3l=sc0.struct.iz3l,
+                       ext3d=sc0.ext3d, omg3d=sc0.omg3d, apf3d=sc0.apf3d, abs3d=a3, sfc_type=1, sfc_param=(0.1, 0, 0, 0, 0),
+                       src_the=sc0.struct.src_the, src_phi=sc0.struct.src_phi, sensors=[dict(the=180.0, phi=270.0, nxr=16, nyr=12)])
+    nslab = 8
+    opt = abi.make_options(target=abi.TARGET_RADIANCE | abi.TARGET_FLUX | abi.TARGET_HEATING, nslab=nslab, wmin=0.2)
+    jobs, keep = scenes.multi_seed_jobs(200000, nslab)
+    g, c = run_both(solver, sc, opt, jobs)
+    check_energy(g['stats'])
+    n = g['stats']['photons']
+    ag, ac = g['stats']['w_atm_abs'] / n, c['stats']['w_atm_abs'] / c['stats']['photons']
+    assert ag > 0.01                                                     # the field does absorb
+    assert abs(ag / ac - 1.0) < 0.01, (ag, ac)
+    z, gm, cm = zscores(g['rad'], c['rad'], nslab, (12, 16))
+    assert_pixels(z, nslab)
+    assert mean_close(g['rad'], c['rad'], nslab)
+    for var in range(3):
+        assert mean_close(g['flux'][:, var], c['flux'][:, var], nslab)
+    gh = g['heat'].reshape(nslab, sc.struct.nz, -1).mean(axis=(0, 2))
+    ch = c['heat'].reshape(nslab, sc.struct.nz, -1).mean(axis=(0, 2))
+    lay = ch > 1e-4 * ch.max()
+    assert np.all(np.abs(gh[lay] / ch[lay] - 1.0) < 0.02), np.max(np.abs(gh[lay] / ch[lay] - 1.0))
+    with pytest.raises(OSError, match='Atm_abst3d must be finite'):
+        bad = a3.copy(); bad[0, 0, 0] = -1e-4
+        solver.upload_scene(abi.HostScene(sc0.zgrd, sc0.ext1d, sc0.omg1d, sc0.apf1d, nx=16, ny=12, dx=100.0, dy=100.0, iz3l=sc0.struct.iz3l,
+                                          ext3d=sc0.ext3d, omg3d=sc0.omg3d, apf3d=sc0.apf3d, abs3d=bad), opt)

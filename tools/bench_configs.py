@@ -64,8 +64,14 @@ def main():
         n = sum(p['photons'] for p in parts)
         ms = sum(p['kernel_ms'] for p in parts)
         b = sum(p['bytes_alg'] for p in parts)
+        peak = 6461.5
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        except Exception:
+            pass
         row = dict(config=name, target=kw0['target'], shape=parts[0]['shape'], calls=len(parts), jobs_per_call=parts[0]['njob'], sensors=parts[0]['nrad'], photons=n, kernel_ms=ms,
-                   mphotons_per_s=n / ms / 1e3, bytes_alg_per_photon=b / n, gbs_alg=b / ms / 1e6,
+                   mphotons_per_s=n / ms / 1e3, bytes_alg_per_photon=b / n, gbs_alg=b / ms / 1e6, roofline_frac_hbm=b / ms / 1e6 / peak,
+                   mphotons_per_s_incl_upload=n / (ms + sum(p['upload_ms'] for p in parts)) / 1e3,
                    max_abs_balance=max(abs(p['balance']) for p in parts), upload_ms=sum(p['upload_ms'] for p in parts),
                    per_photon=parts[0]['per_photon'])
         rows.append(row)

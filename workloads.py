@@ -48,7 +48,7 @@ def c1(scale=1.0, photons=1e6, hom3d=False):
     return kw, abs0
 
 
-def c2(scale=1.0, photons=1e8, nx=480, ny=480, nz3=100, nrun=3):
+def c2(scale=1.0, photons=1e8, nx=480, ny=480, nz3=100, nrun=3, parts=False):
     from er3t_b200.pre import atm_atmmod, abs_16g, pha_mie_wc, cld_gen_les
     from er3t_b200.rtm.mca import mca_atm_1d, mca_atm_3d, mca_sca
     s = np.sqrt(scale)
@@ -66,6 +66,8 @@ def c2(scale=1.0, photons=1e8, nx=480, ny=480, nz3=100, nrun=3):
               sensor_zenith_angle=0.0, sensor_azimuth_angle=0.0, sensor_altitude=705000.0, fdir='tmp-data/c2',
               Nrun=nrun, photons=max(1e4, photons * scale), weights=abs0.coef['weight']['data'], solver='3D', quiet=True, seed=SEED,
               iz3l_fix=True)
+    if parts:
+        return kw, abs0, dict(cld=cld0, atm=atm0, pha=pha0)
     return kw, abs0
 
 
@@ -129,7 +131,7 @@ def c4(scale=1.0, photons=1e9, nwvl=8):
     return out
 
 
-def c5(scale=1.0, photons=1e7):
+def c5(scale=1.0, photons=1e7, segment=0, pha0=None):
     """Flux with gas absorption over a Cox-Munk ocean (cal_ocean_brdf(745 nm, u10 = 5 m/s), er3t/pre/sfc/util.py:14-150)
     under broken 3-D clouds; one flight segment of projects/03_spns_flux-sim.py (2 km pixels, 1 km levels)."""
     from er3t_b200.pre import atm_atmmod, abs_16g, pha_mie_wc, cld_gen_les, sfc_2d_gen, cal_ocean_brdf
@@ -139,8 +141,8 @@ def c5(scale=1.0, photons=1e7):
     atm0 = atm_atmmod(levels=np.arange(0.0, 20.1, 1.0))
     abs0 = abs_16g(wavelength=745.0, atm_obj=atm0, tau_max=1.0)
     cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=2.0, dy=2.0, altitude=np.array([1.5, 2.5, 3.5]), cloud_frac=0.5, corr_km=12.0,
-                       cot_median=12.0, seed=5, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=745.0)
+                       cot_median=12.0, seed=5 + 31 * segment, atm_obj=atm0)
+    pha0 = pha_mie_wc(wavelength=745.0) if pha0 is None else pha0
     oc = cal_ocean_brdf(wvl=745.0, u10=np.full((nx, ny), 5.0))
     sfc0 = sfc_2d_gen(sfc_2d=oc)
     kw = dict(date=DATE, atm_1ds=[mca_atm_1d(atm_obj=atm0, abs_obj=abs0)],
@@ -151,8 +153,29 @@ def c5(scale=1.0, photons=1e7):
     return kw, abs0
 
 
+def c5_segments(scale=1.0, photons=1e7, nseg=30):
+    """The ~30 flight-track segments of projects/03_spns_flux-sim.py:48-53: one independent scene (own cloud field) and
+    one mcarats_ng call per segment, 1e7 photons each.  Returns a LIST of (kw, abs) pairs like c4."""
+    from er3t_b200.pre import pha_mie_wc
+    pha0 = pha_mie_wc(wavelength=745.0)
+    return [c5(scale, photons, segment=i, pha0=pha0) for i in range(nseg)]
+
+
 def build(name, scale=1.0, **kw):
+    """C1 ... C5, plus the variants SURVEY.md 8d names: C1H (2 x 2-column homogeneous-3-D variant of C1), C2R (C2 as the
+    reference runs it: 10 layers of 400 m, L2-resident), C3V1 / C3V9 (one view -- what the reference traces per call --
+    and nine views 0 ... 60 deg in one pass), C5S (30 flight segments, one scene each)."""
     name = name.upper()
+    if name == 'C1H':
+        return c1(scale, hom3d=True, **kw)
+    if name == 'C2R':
+        return c2(scale, nz3=10, **kw)
+    if name == 'C3V1':
+        return c3(scale, views=((0.0, 0.0),), **kw)
+    if name == 'C3V9':
+        return c3(scale, views=tuple((7.5 * i, 40.0 * i) for i in range(9)), **kw)
+    if name == 'C5S':
+        return c5_segments(scale, **kw)
     if name == 'C1':
         return c1(scale, **kw)
     if name == 'C2':
