@@ -97,6 +97,7 @@ struct DevScene {
     // small flux / heating tallies (plane-parallel and few-column scenes) are kept per block in shared memory and flushed
     // once: all photons would otherwise hammer the same few L2 addresses
     int ntal_flux_smem, ntal_heat_smem;   // doubles of the whole flux / heating tally held in shared memory (0: global atomics)
+    int ntal_rad_smem;        // doubles of the whole radiance tally held in shared memory (tiny sensors: 1 x 1-pixel views)
     int tal_per_warp;         // 1: every warp of a block keeps its own copy (very small tallies), 0: one copy per block
     // small 1-D tables (global copies; staged into shared memory by the transport kernel)
     const float* zgrd;        // [nz+1]
@@ -348,6 +349,7 @@ struct Smem {
     double* acc_atm;      // atmospheric absorption: one slot per thread
     double* ftal;         // block- or warp-private flux tally (same layout as the global one) or nullptr
     double* htal;         // block- or warp-private heating tally or nullptr
+    double* rtal;         // block- or warp-private radiance tally or nullptr
     int tal_mode;         // 1: one copy per block (shared atomics); 2: one copy per warp (plain read-modify-write)
     unsigned* cnt;        // event counters [8][32]: one slot per lane and block (flushed to 64-bit totals per block)
 };
@@ -565,6 +567,21 @@ __device__ __forceinline__ void heat_add(const DevScene& S, const Smem& sm, cons
     else { tally_add(S.heat + idx, v); ++n_tal; }
 }
 
+// one flux / heating tally of a photon whose position is in metres (p.x, p.y)
+__device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev, unsigned& n_tal) {
+    const TallyCtx t = tally_ctx(S, p.job);
+    flux_add(S, sm, t, var, lev, tally_col_m(S, p), p.w, n_tal);
+}
+__device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep, unsigned& n_tal) {
+    const TallyCtx t = tally_ctx(S, p.job);
+    heat_add(S, sm, t, iz, tally_col_m(S, p), dep, n_tal);
+}
+// radiance tally (idx: position inside the whole radiance tally)
+__device__ __forceinline__ void rad_add(const DevScene& S, const Smem& sm, size_t idx, double v, unsigned& n_tal) {
+    if (sm.rtal) tally_agg(sm.rtal + idx, v, sm.tal_mode);
+    else { tally_add(S.rad + idx, v); ++n_tal; }
+}
+
 // layer that contains z among layers [l0, l1)
 __device__ __forceinline__ int find_layer(const Smem& sm, int l0, int l1, float z) {
     int lo = l0, hi = l1 - 1;
@@ -743,7 +760,7 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
 
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
 __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, float fw,
-                                           int fx, int fy, float s3) {
+                                           int fx, int fy, float s3, unsigned& n_tal) {
     const float tau = le_tau(S, sm, se, p, fx, fy, s3);
     const float contrib = fw * __expf(-tau) * se.inv_sz;
     int px, py;
@@ -757,9 +774,8 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
         py = min(se.nyr - 1, max(0, int(yr * S.inv_Ly * float(se.nyr))));
     }
     const DevJob& J = S.jobs[p.job];
-    tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
+    rad_add(S, sm, size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix, n_tal);
     CNT_ADD(CNT_LE, 1u);
-    CNT_ADD(CNT_TALLY, 1u);
 }
 
 // All-sky camera (Rad_mrkind = 1): contribution of one event, per unit photon weight, to the radiance the camera at
@@ -880,7 +896,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         double* acc = reinterpret_cast<double*>(q4);
         double* acc_atm = acc + 4 * 32;
         double* tal = acc_atm + blockDim.x;
-        const int ntal = PL ? S.ntal_flux_smem + S.ntal_heat_smem : 0;
+        // private tallies: one copy per block (shared atomics) or one per warp (tal_per_warp)
+        const int ntal1 = (PL ? S.ntal_flux_smem + S.ntal_heat_smem : 0) + S.ntal_rad_smem;
+        const int ntal = ntal1 * (S.tal_per_warp ? int(blockDim.x >> 5) : 1);
         unsigned* cnt = reinterpret_cast<unsigned*>(tal + ntal);
         float* q = reinterpret_cast<float*>(cnt + 8 * 32);
         float* z = q; q += S.nz + 1;
@@ -918,8 +936,14 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         }
         acc_atm[threadIdx.x] = 0.0;
         for (int i = threadIdx.x; i < ntal; i += blockDim.x) tal[i] = 0.0;
-        sm.ftal = (PL && S.ntal_flux_smem > 0) ? tal : nullptr;
-        sm.htal = (PL && S.ntal_heat_smem > 0) ? tal + S.ntal_flux_smem : nullptr;
+        {
+            double* mine = tal + (S.tal_per_warp ? warp * ntal1 : 0);
+            const int nf = PL ? S.ntal_flux_smem : 0, nh = PL ? S.ntal_heat_smem : 0;
+            sm.ftal = nf > 0 ? mine : nullptr;
+            sm.htal = nh > 0 ? mine + nf : nullptr;
+            sm.rtal = S.ntal_rad_smem > 0 ? mine + nf + nh : nullptr;
+            sm.tal_mode = S.tal_per_warp ? 2 : 1;
+        }
         for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
         sm.z = z; sm.e1tot = e1tot; sm.e1cum = e1cum; sm.e1 = e1; sm.o1 = o1; sm.a1 = a1;
         sm.slabA = slabA; sm.slabB = slabB; sm.grpA = grpA; sm.grpB = grpB; sm.acc = acc; sm.acc_atm = acc_atm; sm.cnt = cnt;
@@ -934,7 +958,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
     const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
     const int nxy = S.nx * S.ny;
 
-    unsigned n_cell = 0;
+    unsigned n_cell = 0, n_tal = 0;
     // queue lengths (warp-uniform): DEAD, FLY, TENTATIVE (+ escapes), COLLISION, SURFACE.  Queues are LIFO stacks of slot numbers.
     // Once the photon counter is exhausted nD becomes a large negative number: the dead queue never wins again and is no
     // longer written.
@@ -979,6 +1003,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const bool have = lane < n;
             const int slot = have ? int(qD[nD - 1 - lane]) : 0;
             nD -= n;
+            __syncwarp();                       // queue entries are read before any lane pushes (memory ordering, not just convergence)
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)n);
             base = __shfl_sync(FULL, base, 0);
@@ -1013,7 +1038,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 }
                 p.tau = -__logf(v.x);
                 CNT_ADD(CNT_PHOT, 1u);
-                if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
+                if (want_flux) { flux_tally(S, sm, p, 0, S.nz, n_tal); flux_tally(S, sm, p, 1, S.nz, n_tal); }
                 pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
             QPUSH(qF, nF, born, slot);
@@ -1032,6 +1057,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const bool have = lane < n;
             const int slot = have ? int(qF[nF - 1 - lane]) : 0;
             nF -= n;
+            __syncwarp();
             if (have) pool_load_flight<NP, PL>(pool, slot, p);
             const bool frozen = FZ && (p.flags & FL_FROZEN);
             // direction per fine cell; zero components are replaced by a tiny value (no special cases in the loop)
@@ -1105,7 +1131,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
+                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn), n_tal);
                         }
                         p.w = wn;
                     }
@@ -1143,10 +1169,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         fl &= ~FL_STALE;
                         if (PL && want_flux) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            if (upz) flux_tally(S, sm, p, 2, p.is + 1);
+                            if (upz) flux_tally(S, sm, p, 2, p.is + 1, n_tal);
                             else {
-                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is);
-                                flux_tally(S, sm, p, 1, p.is);
+                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is, n_tal);
+                                flux_tally(S, sm, p, 1, p.is, n_tal);
                             }
                         }
                         const int nis = upz ? shi : slo - 1;
@@ -1179,6 +1205,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 slot = e & 255; ev = e >> 8;
             }
             nE -= n;
+            __syncwarp();
             if (have) pool_load<NP>(pool, slot, p, S.Sx, S.Sy);
             bool accepted = false, rejected = false;
             float c_apf = 0.0f, c_uz = 0.0f, c_uw = 0.0f, c_s3 = 0.0f;
@@ -1262,7 +1289,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     const float wn = p.w * omg;
                     if (wn < p.w) {
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
+                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn), n_tal);
                     }
                     p.w = wn;
                     p.order++; p.flags &= ~FL_DIRECT;
@@ -1289,6 +1316,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         int n, slot = 0;
         if (phase == 3) { n = min(nC, 32); if (lane < n) slot = int(qC[nC - 1 - lane]); nC -= n; }
         else { n = min(nS, 32); if (lane < n) slot = int(qS[nS - 1 - lane]); nS -= n; }
+        __syncwarp();
         const bool have = lane < n;
         float c_uw = 0.0f;
         if (have) { pool_load<NP>(pool, slot, p, S.Sx, S.Sy); c_uw = pool[F_AUX * NP + slot]; }
@@ -1364,9 +1392,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         CNT_ADD(CNT_VISIT, nv);
                         if (c > 0.0f) {
                             const DevJob& J = S.jobs[p.job];
-                            tally_add(S.rad + size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
+                            rad_add(S, sm, size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix, n_tal);
                             CNT_ADD(CNT_LE, 1u);
-                            CNT_ADD(CNT_TALLY, 1u);
                         }
                         continue;
                     }
@@ -1379,7 +1406,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     } else {
                         f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, se.s) * se.s.z : 0.0f;
                     }
-                    if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3);
+                    if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3, n_tal);
                 }
             }
 
@@ -1403,7 +1430,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             }
             p.d = newd;
             if (evk == EV_SFC) {
-                if (want_flux) flux_tally(S, sm, p, 2, 0);
+                if (want_flux) flux_tally(S, sm, p, 2, 0, n_tal);
                 if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && (p.flags & FL_FROZEN))) {
                     p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                     p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
@@ -1433,15 +1460,22 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #undef QPUSH_DEAD
 
     // ---- flush the block-private tallies (one global atomic per non-zero entry and block)
-    if (PL && (sm.ftal || sm.htal)) {
+    if (sm.ftal || sm.htal || sm.rtal) {
         __syncthreads();
-        for (int i = threadIdx.x; i < S.ntal_flux_smem; i += blockDim.x) {
-            const double v = sm.ftal[i];
-            if (v != 0.0) { tally_add(S.flux + i, v); CNT_ADD(CNT_TALLY, 1u); }
-        }
-        for (int i = threadIdx.x; i < S.ntal_heat_smem; i += blockDim.x) {
-            const double v = sm.htal[i];
-            if (v != 0.0) { tally_add(S.heat + i, v); CNT_ADD(CNT_TALLY, 1u); }
+        const int nf = (PL && sm.ftal) ? S.ntal_flux_smem : 0, nh = (PL && sm.htal) ? S.ntal_heat_smem : 0, nr = S.ntal_rad_smem;
+        const int ntal1 = nf + nh + nr;
+        const int ncopy = S.tal_per_warp ? int(blockDim.x >> 5) : 1;
+        // every warp computed its own `mine`; copy 0 starts where warp 0's (or the block's) copy does
+        const double* tal0 = (sm.ftal ? sm.ftal : (sm.htal ? sm.htal : sm.rtal)) - (S.tal_per_warp ? (threadIdx.x >> 5) * ntal1 : 0);
+        for (int i = threadIdx.x; i < ntal1; i += blockDim.x) {
+            double v = 0.0;
+            for (int c = 0; c < ncopy; ++c) v += tal0[c * ntal1 + i];
+            if (v != 0.0) {
+                if (i < nf) tally_add(S.flux + i, v);
+                else if (i < nf + nh) tally_add(S.heat + (i - nf), v);
+                else tally_add(S.rad + (i - nf - nh), v);
+                ++n_tal;
+            }
         }
     }
     // ---- flush the event counters and energy sums: the cell counter lives in a register (one atomic per warp), the rest
@@ -1450,6 +1484,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         unsigned long long v = n_cell;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
         if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(S.stats) + 1, v);
+        v = n_tal;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(S.stats) + 7, v);
         double a = sm.acc_atm[threadIdx.x];
         for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(FULL, a, o);
         if (lane == 0) atomicAdd(&S.stats->w_atm, a);
@@ -2083,8 +2120,16 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.counter = (unsigned long long*)H->counter.p; S.stats = (DevStats*)H->stats.p;
 
     // block-private tallies when the whole flux + heating tally is small (plane-parallel / few-column scenes)
-    S.ntal_flux_smem = 0; S.ntal_heat_smem = 0;
-    if (per_level && H->nflux + H->nheat <= 2048 && opt->smem_tally >= 0) { S.ntal_flux_smem = int(H->nflux); S.ntal_heat_smem = int(H->nheat); }
+    // (smem_tally: < 0 off; 0 auto = one copy per block, warp-aggregated shared atomics; 2 = one copy per warp when that
+    // fits 24 KB, plain read-modify-write after the aggregation)
+    S.ntal_flux_smem = 0; S.ntal_heat_smem = 0; S.ntal_rad_smem = 0; S.tal_per_warp = 0;
+    if (opt->smem_tally >= 0) {
+        size_t budget = 2048;
+        if (per_level && H->nflux + H->nheat <= budget) { S.ntal_flux_smem = int(H->nflux); S.ntal_heat_smem = int(H->nheat); budget -= H->nflux + H->nheat; }
+        if (H->nrad > 0 && H->nrad <= std::min<size_t>(budget, 512)) S.ntal_rad_smem = int(H->nrad);
+        const size_t tot = size_t(S.ntal_flux_smem) + S.ntal_heat_smem + S.ntal_rad_smem;
+        if (opt->smem_tally == 2 && tot > 0 && tot * 8 * (RT_TPB / 32) <= 24 * 1024) S.tal_per_warp = 1;
+    }
     H->k_pl = per_level; H->k_fz = (opt->solver != B200RT_SOLVER_3D);
     H->k_cam = false;
     for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
@@ -2200,7 +2245,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
         const bool uz = S.uz_ok != 0;
         transport_fn9 kern = pick_v9(H->k_pl, H->k_fz, H->k_cam, uz, npb);
         const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(V9_NT) * 8 + size_t(V9_POOL_WORDS(npb)) * 4 +
-                            8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
+                            8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
         if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pool + 1-D tables exceed shared memory; lower pool_slots");
         CK(set_smem_attr(H, (const void*)kern, smem));
         const unsigned long long want = (acc + npb - 1) / npb;
@@ -2216,7 +2261,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     int bps = 0;
     transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
-                        8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem);
+                        8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
     CK(set_smem_attr(H, (const void*)kern, smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, tpb, smem));
