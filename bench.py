@@ -13,6 +13,7 @@ One "step" = one complete `mcarats_ng` job set (Nrun x Ng jobs = 3 x 1e8 photons
            numpy arrays: mca_atm_3d(device_props=True) + mcarats_ng + mca_out_ng -- the input builder, scene packing
            (omega / apf derived on the GPU), H2D, transport, D2H and the run statistics are all inside the timed region.
 `strong` : the FIXED 3e8-photon job set sharded over the N ranks (N > 1 only; `value` stays weak-scaled).
+`c4_sweep`: (N > 1) the config-4 wavelength x g sweep sharded over the ranks, photon sharding vs whole wavelengths per rank.
 `accuracy`: error of the GPU path against the deterministic adding-doubling fixture (plane-parallel Mie cloud) and
            against the CPU oracle on a scaled copy of this workload.
 Inputs are larger than L2 (3-D fields 370 MB in HBM vs 126 MB L2), so no explicit L2 flush between iterations.
@@ -220,6 +221,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-accuracy', action='store_true')
+    ap.add_argument('--c4-photons', type=float, default=1e9, help='N > 1: photons of the config-4 sweep leg (0 = skip)')
     ap.add_argument('--sv', type=str, default='0,0,0')
     ap.add_argument('--empty-runs', type=int, default=0, help='A/B switch of the resident leg: -1 = no vertical merging of empty coarse cells')
     args = ap.parse_args()
@@ -276,6 +278,11 @@ def main():
     torch.cuda.set_device(local)
     # weak scaling: every GPU traces the full BASELINE photon count, the job set grows with the number of GPUs
     kw, abs0, parts = build_workload(args.nx, args.nx, args.nz3, args.photons * world, parts=True)
+    # the e2e leg's inputs -- the raw cloud fields -- live in page-locked host memory (the contract's "pinned host
+    # inputs"); mca_atm_3d(device_props=True) hands them to the library without a host copy
+    from er3t_b200.util import pin_array
+    for key in ('extinction', 'cer'):
+        parts['cld'].lay[key]['data'] = pin_array(np.asarray(parts['cld'].lay[key]['data'], dtype=np.float32))
     kw['device'] = local
     kw['supervoxel'] = tuple(int(v) for v in args.sv.split(','))
     kw['shard'] = (rank, world)
@@ -390,6 +397,16 @@ def main():
     if world == 1 and not args.no_accuracy:
         accuracy = accuracy_summary(sol)
 
+    # ---- config-4 sweep sharded over the ranks (N > 1): photon sharding vs whole wavelengths per rank (tools/c4_sweep.py)
+    c4 = None
+    if world > 1 and args.c4_photons > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            from c4_sweep import sweep_both
+            c4 = sweep_both(sol, rank, world, scale=1.0, reps=1, photons=args.c4_photons)
+        except Exception as e:                                 # never lose the headline line to the extra leg
+            c4 = {'error': repr(e)[:300]}
+
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -423,7 +440,7 @@ def main():
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (fp64 tallies)', 'data': 'synthetic', 'config': config,
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-            'photons_per_step': photons_step, 'accuracy': accuracy, 'strong': strong}
+            'photons_per_step': photons_step, 'accuracy': accuracy, 'strong': strong, 'c4_sweep': c4}
     print(json.dumps(line))
 
 

@@ -554,32 +554,36 @@ __device__ __forceinline__ int tally_col_m(const DevScene& S, const Photon& p) {
     return min(S.ny - 1, max(0, int(p.y * S.inv_dy))) * S.nx + min(S.nx - 1, max(0, int(p.x * S.inv_dx)));
 }
 // tal_mode: 0 global atomics, 1 block-private shared tally, 2 warp-private shared tally
-__device__ __forceinline__ void flux_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int var, int lev, int col, float w, unsigned& n_tal) {
+// (updates that reach global memory are counted in the block's shared event counter; private ones at the flush)
+__device__ __forceinline__ void flux_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int var, int lev, int col, float w) {
     const double v = double(w) * __ldg(t.fs + lev);
     const size_t idx = size_t(t.foff) + size_t(var * (S.nz + 1) + lev) * size_t(S.nx * S.ny) + size_t(col);
     if (sm.ftal) tally_agg(sm.ftal + idx, v, sm.tal_mode);
-    else { tally_add(S.flux + idx, v); ++n_tal; }
+    else { tally_add(S.flux + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
-__device__ __forceinline__ void heat_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int iz, int col, double dep, unsigned& n_tal) {
+__device__ __forceinline__ void heat_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int iz, int col, double dep) {
     const double v = dep * __ldg(t.fs + iz);
     const size_t idx = size_t(t.hoff) + size_t(iz) * size_t(S.nx * S.ny) + size_t(col);
     if (sm.htal) tally_agg(sm.htal + idx, v, sm.tal_mode);
-    else { tally_add(S.heat + idx, v); ++n_tal; }
+    else { tally_add(S.heat + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
 
 // one flux / heating tally of a photon whose position is in metres (p.x, p.y)
-__device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev, unsigned& n_tal) {
+__device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
     const TallyCtx t = tally_ctx(S, p.job);
-    flux_add(S, sm, t, var, lev, tally_col_m(S, p), p.w, n_tal);
+    flux_add(S, sm, t, var, lev, tally_col_m(S, p), p.w);
 }
-__device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep, unsigned& n_tal) {
+__device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
     const TallyCtx t = tally_ctx(S, p.job);
-    heat_add(S, sm, t, iz, tally_col_m(S, p), dep, n_tal);
+    heat_add(S, sm, t, iz, tally_col_m(S, p), dep);
 }
-// radiance tally (idx: position inside the whole radiance tally)
-__device__ __forceinline__ void rad_add(const DevScene& S, const Smem& sm, size_t idx, double v, unsigned& n_tal) {
-    if (sm.rtal) tally_agg(sm.rtal + idx, v, sm.tal_mode);
-    else { tally_add(S.rad + idx, v); ++n_tal; }
+// radiance tally (idx: position inside the whole radiance tally).  The block-private copy exists in the per-level (PL)
+// kernels only -- tiny sensors belong to plane-parallel / few-column scenes, which the host routes there -- so that the
+// radiance kernels of the large 3-D scenes carry neither the branch nor the aggregation code.
+template <bool PL>
+__device__ __forceinline__ void rad_add(const DevScene& S, const Smem& sm, size_t idx, double v) {
+    if (PL && sm.rtal) tally_agg(sm.rtal + idx, v, sm.tal_mode);
+    else { tally_add(S.rad + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
 
 // layer that contains z among layers [l0, l1)
@@ -705,6 +709,68 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
         tmz = cz ? fminf(T, (zl[lzc] - za) * isz) : tmz;                      \
         IDX = (lzc * S.ny + fy) * S.nx + fx;                                  \
     }
+#ifdef RT_LE_SPLIT
+    // Two independent chains per ray: the 3-D piece [0, T] is cut in the middle and both halves are marched in the same
+    // loop -- two voxel loads in flight per lane instead of one, half the trip count (the march is bound by the latency of
+    // its dependent gathers).  Chain B starts from the POSITION at T / 2; both chains cover their half exactly.
+    const float Tfull = T;
+    const bool split = Tfull * (fabsf(se.s.x) * S.inv_dx + fabsf(se.s.y) * S.inv_dy) + float(S.nz3) * fabsf((ze - za) / (zb1 - zb0)) >= 4.0f;
+    const float tB = 0.5f * Tfull;
+    // chain B state
+    float xB = wrapf(x + se.s.x * tB, S.Lx, S.inv_Lx), yB = wrapf(y + se.s.y * tB, S.Ly, S.inv_Ly);
+    const float zB = za + se.s.z * tB;
+    int fxB = min(S.nx - 1, max(0, int(xB * S.inv_dx))), fyB = min(S.ny - 1, max(0, int(yB * S.inv_dy)));
+    int lzB = lz;
+    while (lzB + dl != lzend && (up ? zB >= zl[lzB] : zB <= zl[lzB])) lzB += dl;
+    float tmxB = se.s.x != 0.0f ? tB + fmaxf(0.0f, (float(fxB + (px ? 1 : 0)) * S.dx - xB) * isx) : RT_INF;
+    float tmyB = se.s.y != 0.0f ? tB + fmaxf(0.0f, (float(fyB + (py ? 1 : 0)) * S.dy - yB) * isy) : RT_INF;
+    float tmzB = fminf(Tfull, (zl[lzB] - za) * isz);
+    float tBcur = tB;
+    // chain A ends where B starts
+    const float TA = split ? tB : Tfull;
+    tmz = fminf(TA, tmz);
+    bool dA = false, dB = !split;
+    float eA = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
+    float eB = split ? __ldg(base + (lzB * S.ny + fyB) * S.nx + fxB) : 0.0f;
+#define LE_STEP2(TM_X, TM_Y, TM_Z, TT, FX, FY, LZ, TEND, SEG, IDX, DONE)      \
+    {                                                                         \
+        const float tn = fminf(fminf(TM_X, TM_Y), TM_Z);                      \
+        SEG = tn - TT;                                                        \
+        TT = tn;                                                              \
+        const bool cx = TM_X <= TM_Y && TM_X <= TM_Z;                         \
+        const bool cy = !cx && TM_Y <= TM_Z;                                  \
+        const bool cz = !(cx || cy);                                          \
+        int nfx = FX + sx, nfy = FY + sy;                                     \
+        nfx = nfx >= S.nx ? 0 : (nfx < 0 ? S.nx - 1 : nfx);                   \
+        nfy = nfy >= S.ny ? 0 : (nfy < 0 ? S.ny - 1 : nfy);                   \
+        FX = cx ? nfx : FX;                                                   \
+        FY = cy ? nfy : FY;                                                   \
+        LZ = cz ? LZ + dl : LZ;                                               \
+        TM_X = cx ? TM_X + tdx : TM_X;                                        \
+        TM_Y = cy ? TM_Y + tdy : TM_Y;                                        \
+        DONE = tn >= TEND || LZ == lzend;                                     \
+        const int lzc = min(S.nz3 - 1, max(0, LZ));                           \
+        TM_Z = cz ? fminf(TEND, (zl[lzc] - za) * isz) : TM_Z;                 \
+        IDX = (lzc * S.ny + FY) * S.nx + FX;                                  \
+    }
+    for (;;) {
+        float segA, segB;
+        int iA, iB;
+        bool nA, nB;
+        LE_STEP2(tmx, tmy, tmz, t, fx, fy, lz, TA, segA, iA, nA);
+        LE_STEP2(tmxB, tmyB, tmzB, tBcur, fxB, fyB, lzB, Tfull, segB, iB, nB);
+        n_visit += (dA ? 0u : 1u) + (dB ? 0u : 1u);
+        segA = dA ? 0.0f : segA; segB = dB ? 0.0f : segB;
+        nA = nA || dA; nB = nB || dB;
+        const float enA = nA ? 0.0f : __ldg(base + iA);
+        const float enB = nB ? 0.0f : __ldg(base + iB);
+        tau3 = fmaf(eA, segA, tau3);
+        tau3 = fmaf(eB, segB, tau3);
+        if (nA && nB) break;
+        eA = enA; eB = enB; dA = nA; dB = nB;
+    }
+#undef LE_STEP2
+#else
     float e = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
     for (;;) {
         float seg;
@@ -716,6 +782,7 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
         if (done) break;
         e = en;
     }
+#endif
 #undef LE_STEP
     *n_visit_out = n_visit;
     return tau + tau3;
@@ -750,6 +817,9 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
         }
         return fmaxf(0.0f, t1) * se.inv_sz;
     }
+#ifdef RT_NO_GENERIC_LE      /* experiment switch: kernels without the oblique-view march (valid for vertical views only) */
+    return 0.0f;
+#endif
     if (frozen) { fx = p.cix; fy = p.ciy; }
     unsigned nv = 0;
     const RayTarget rt = {se.s, se.zt, se.lt};
@@ -759,8 +829,9 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
 }
 
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
+template <bool PL>
 __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, float fw,
-                                           int fx, int fy, float s3, unsigned& n_tal) {
+                                           int fx, int fy, float s3) {
     const float tau = le_tau(S, sm, se, p, fx, fy, s3);
     const float contrib = fw * __expf(-tau) * se.inv_sz;
     int px, py;
@@ -774,7 +845,7 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
         py = min(se.nyr - 1, max(0, int(yr * S.inv_Ly * float(se.nyr))));
     }
     const DevJob& J = S.jobs[p.job];
-    rad_add(S, sm, size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix, n_tal);
+    rad_add<PL>(S, sm, size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
     CNT_ADD(CNT_LE, 1u);
 }
 
@@ -859,6 +930,17 @@ __device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, f
     return fac;
 }
 
+// which of several 3-D components scatters (np3d > 1 only; cold for the single-component scenes er3t builds, so out of line)
+__device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, const float2* __restrict__ prop3, int np3d, size_t n3,
+                                               unsigned vox, float uc) {
+    for (int k = 0; k < np3d; ++k) {
+        const float e = __ldg(ext3 + size_t(k) * n3 + vox);
+        if (uc < e || k == np3d - 1) return __ldg(prop3 + size_t(k) * n3 + vox);
+        uc -= e;
+    }
+    return make_float2(1.0f, 0.0f);
+}
+
 // Persistent-thread photon transport with queue-based path regeneration.
 //
 // Every WARP owns a pool of NP photon slots in shared memory (NP = 3 x the warp width by default) and every slot is in
@@ -880,7 +962,11 @@ __device__ __noinline__ float surface_sample(int sfc_type, float p0, float p1, f
 // only synchronisation is __syncwarp.
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
-template <bool PL, bool FZ, int NP, bool CAM>
+// UZ: the 3-D layers are equally thick and vertical runs of empty cells are on (S.uz_ok): the fine slab of a photon that
+//     left a box sideways follows from its height, and the layer search for unequal layers is not part of the flight
+//     loop at all.  Measured on config 2: the ~35 never-executed instructions of that search cost 3.4 % (the loop is
+//     instruction-fetch sensitive, profiles/README.md r02_f), hence a template parameter instead of a run-time test.
+template <bool PL, bool FZ, int NP, bool CAM, bool UZ>
 __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
     Smem sm;
@@ -897,7 +983,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         double* acc_atm = acc + 4 * 32;
         double* tal = acc_atm + blockDim.x;
         // private tallies: one copy per block (shared atomics) or one per warp (tal_per_warp)
-        const int ntal1 = (PL ? S.ntal_flux_smem + S.ntal_heat_smem : 0) + S.ntal_rad_smem;
+        const int ntal1 = PL ? S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem : 0;
         const int ntal = ntal1 * (S.tal_per_warp ? int(blockDim.x >> 5) : 1);
         unsigned* cnt = reinterpret_cast<unsigned*>(tal + ntal);
         float* q = reinterpret_cast<float*>(cnt + 8 * 32);
@@ -941,7 +1027,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const int nf = PL ? S.ntal_flux_smem : 0, nh = PL ? S.ntal_heat_smem : 0;
             sm.ftal = nf > 0 ? mine : nullptr;
             sm.htal = nh > 0 ? mine + nf : nullptr;
-            sm.rtal = S.ntal_rad_smem > 0 ? mine + nf + nh : nullptr;
+            sm.rtal = (PL && S.ntal_rad_smem > 0) ? mine + nf + nh : nullptr;
             sm.tal_mode = S.tal_per_warp ? 2 : 1;
         }
         for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
@@ -958,13 +1044,18 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
     const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
     const int nxy = S.nx * S.ny;
 
-    unsigned n_cell = 0, n_tal = 0;
+    unsigned n_cell = 0;
     // queue lengths (warp-uniform): DEAD, FLY, TENTATIVE (+ escapes), COLLISION, SURFACE.  Queues are LIFO stacks of slot numbers.
     // Once the photon counter is exhausted nD becomes a large negative number: the dead queue never wins again and is no
     // longer written.
     int nD = NP, nF = 0, nE = 0, nC = 0, nS = 0;
     const int ND_DONE = -(1 << 29);
 
+#ifdef RT_NO_POP_SYNC
+#define POP_SYNC()
+#else
+#define POP_SYNC() __syncwarp()
+#endif
 #define RNG4(out)                                                                                     \
     {                                                                                                 \
         const unsigned long long seed_ = S.jobs[p.job].seed;                                          \
@@ -1003,7 +1094,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const bool have = lane < n;
             const int slot = have ? int(qD[nD - 1 - lane]) : 0;
             nD -= n;
-            __syncwarp();                       // queue entries are read before any lane pushes (memory ordering, not just convergence)
+            POP_SYNC();                         // queue entries are read before any lane pushes (memory ordering, not just convergence)
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)n);
             base = __shfl_sync(FULL, base, 0);
@@ -1038,7 +1129,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 }
                 p.tau = -__logf(v.x);
                 CNT_ADD(CNT_PHOT, 1u);
-                if (want_flux) { flux_tally(S, sm, p, 0, S.nz, n_tal); flux_tally(S, sm, p, 1, S.nz, n_tal); }
+                if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
                 pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
             QPUSH(qF, nF, born, slot);
@@ -1057,7 +1148,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const bool have = lane < n;
             const int slot = have ? int(qF[nF - 1 - lane]) : 0;
             nF -= n;
-            __syncwarp();
+            POP_SYNC();
             if (have) pool_load_flight<NP, PL>(pool, slot, p);
             const bool frozen = FZ && (p.flags & FL_FROZEN);
             // direction per fine cell; zero components are replaced by a tiny value (no special cases in the loop)
@@ -1078,7 +1169,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
                 if (have && ev == EV_NONE) {
-                    if (!PL && S.uz_ok && (p.flags & FL_STALE)) {
+                    if (!PL && UZ && (p.flags & FL_STALE)) {
                         // left a box of several fine slabs sideways: the slab follows from the height
                         p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
                         p.flags &= ~FL_STALE;
@@ -1088,8 +1179,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     bool in3 = aw >= 0;
                     // one look-up gives both the fine-cell majorant and (sign bit) "the enclosing coarse cell is empty"
                     float mj = -1.0f;
-                    if (in3) { mj = __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix); ++n_cell; }
-                    if (!PL && mj >= 0.0f && (p.flags & FL_STALE)) {
+                    if (in3) { mj = __ldg(majp + unsigned(((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix)); ++n_cell; }
+                    if (!PL && !UZ && mj >= 0.0f && (p.flags & FL_STALE)) {
                         // (3-D layers of unequal thickness only; boxes never span more than one z group then)
                         // entered a non-empty coarse cell sideways: find the fine z slab of the current height
                         const int gw = __float_as_int(sm.grpA[(aw >> 16) & 0x7fff].w);
@@ -1100,7 +1191,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         }
                         p.is = lo;
                         A = sm.slabA[lo]; aw = __float_as_int(A.w);
-                        mj = fmaxf(0.0f, __ldg(majp + ((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix));
+                        mj = fmaxf(0.0f, __ldg(majp + unsigned(((aw & 0xffff) * ncy + p.ciy) * ncx + p.cix)));
                     }
                     const bool empty = mj < 0.0f;                       // 1-D slabs count as empty
                     // empty boxes span the z groups glo ... ghi: the run of empty coarse cells encoded in the look-up
@@ -1131,7 +1222,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn), n_tal);
+                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
                         }
                         p.w = wn;
                     }
@@ -1169,10 +1260,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         fl &= ~FL_STALE;
                         if (PL && want_flux) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            if (upz) flux_tally(S, sm, p, 2, p.is + 1, n_tal);
+                            if (upz) flux_tally(S, sm, p, 2, p.is + 1);
                             else {
-                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is, n_tal);
-                                flux_tally(S, sm, p, 1, p.is, n_tal);
+                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is);
+                                flux_tally(S, sm, p, 1, p.is);
                             }
                         }
                         const int nis = upz ? shi : slo - 1;
@@ -1205,7 +1296,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 slot = e & 255; ev = e >> 8;
             }
             nE -= n;
-            __syncwarp();
+            POP_SYNC();
             if (have) pool_load<NP>(pool, slot, p, S.Sx, S.Sy);
             bool accepted = false, rejected = false;
             float c_apf = 0.0f, c_uz = 0.0f, c_uw = 0.0f, c_s3 = 0.0f;
@@ -1225,7 +1316,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 RNG4(u);
                 {
                     // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
-                    const bool by_height = !PL && S.uz_ok && ev_empty && ev_in3;     // the box may span several z groups
+                    const bool by_height = !PL && UZ && ev_empty && ev_in3;     // the box may span several z groups
                     if (by_height) p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
                     const int4 sb = sm.slabB[p.is];
                     int l0 = sb.x, l1 = sb.y;
@@ -1235,7 +1326,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 const int izn = p.iz;
                 float sig = sm.e1tot[izn];
                 float s3 = 0.0f;
-                int fx = 0, fy = 0, vox = 0;
+                int fx = 0, fy = 0;
+                unsigned vox = 0;
                 if (ev_in3) {
                     if (frozen) { fx = p.cix; fy = p.ciy; }
                     else {
@@ -1245,7 +1337,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         fx = min(min(S.nx, ixhi * S.svx) - 1, max(ixlo * S.svx, int(p.x * S.inv_dx)));
                         fy = min(min(S.ny, iyhi * S.svy) - 1, max(iylo * S.svy, int(p.y * S.inv_dy)));
                     }
-                    vox = ((izn - S.iz0) * S.ny + fy) * S.nx + fx;
+                    vox = unsigned(((izn - S.iz0) * S.ny + fy) * S.nx + fx);
                     if (!ev_empty) { s3 = __ldg(S.ext3tot + vox); sig += s3; CNT_ADD(CNT_TENT, 1u); }
                 }
                 p.tau = -__logf(u.y);
@@ -1266,16 +1358,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                             const float2 pr = __ldg(S.prop3 + vox);
                             omg = pr.x; apf = pr.y; found = true;
                         } else {
-                            const size_t n3 = size_t(S.nz3) * nxy;
-                            for (int k = 0; k < S.np3d; ++k) {
-                                const float e = __ldg(S.ext3 + size_t(k) * n3 + vox);
-                                if (uc < e || k == S.np3d - 1) {
-                                    const float2 pr = __ldg(S.prop3 + size_t(k) * n3 + vox);
-                                    omg = pr.x; apf = pr.y; found = true;
-                                    break;
-                                }
-                                uc -= e;
-                            }
+                            const float2 pr = pick_component3(S.ext3, S.prop3, S.np3d, size_t(S.nz3) * nxy, vox, uc);
+                            omg = pr.x; apf = pr.y; found = true;
                         }
                     } else uc -= s3;
                     if (!found) {
@@ -1289,7 +1373,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     const float wn = p.w * omg;
                     if (wn < p.w) {
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn), n_tal);
+                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
                     }
                     p.w = wn;
                     p.order++; p.flags &= ~FL_DIRECT;
@@ -1316,7 +1400,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         int n, slot = 0;
         if (phase == 3) { n = min(nC, 32); if (lane < n) slot = int(qC[nC - 1 - lane]); nC -= n; }
         else { n = min(nS, 32); if (lane < n) slot = int(qS[nS - 1 - lane]); nS -= n; }
-        __syncwarp();
+        POP_SYNC();
         const bool have = lane < n;
         float c_uw = 0.0f;
         if (have) { pool_load<NP>(pool, slot, p, S.Sx, S.Sy); c_uw = pool[F_AUX * NP + slot]; }
@@ -1392,7 +1476,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         CNT_ADD(CNT_VISIT, nv);
                         if (c > 0.0f) {
                             const DevJob& J = S.jobs[p.job];
-                            rad_add(S, sm, size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix, n_tal);
+                            rad_add<PL>(S, sm, size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
                             CNT_ADD(CNT_LE, 1u);
                         }
                         continue;
@@ -1406,7 +1490,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     } else {
                         f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, se.s) * se.s.z : 0.0f;
                     }
-                    if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3, n_tal);
+                    if (f > 0.0f) le_deposit<PL>(S, sm, se, p, f * p.w, fx, fy, s3);
                 }
             }
 
@@ -1430,7 +1514,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             }
             p.d = newd;
             if (evk == EV_SFC) {
-                if (want_flux) flux_tally(S, sm, p, 2, 0, n_tal);
+                if (want_flux) flux_tally(S, sm, p, 2, 0);
                 if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && (p.flags & FL_FROZEN))) {
                     p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                     p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
@@ -1460,9 +1544,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #undef QPUSH_DEAD
 
     // ---- flush the block-private tallies (one global atomic per non-zero entry and block)
-    if (sm.ftal || sm.htal || sm.rtal) {
+    if (PL && (sm.ftal || sm.htal || sm.rtal)) {
         __syncthreads();
-        const int nf = (PL && sm.ftal) ? S.ntal_flux_smem : 0, nh = (PL && sm.htal) ? S.ntal_heat_smem : 0, nr = S.ntal_rad_smem;
+        const int nf = sm.ftal ? S.ntal_flux_smem : 0, nh = sm.htal ? S.ntal_heat_smem : 0, nr = S.ntal_rad_smem;
         const int ntal1 = nf + nh + nr;
         const int ncopy = S.tal_per_warp ? int(blockDim.x >> 5) : 1;
         // every warp computed its own `mine`; copy 0 starts where warp 0's (or the block's) copy does
@@ -1474,7 +1558,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 if (i < nf) tally_add(S.flux + i, v);
                 else if (i < nf + nh) tally_add(S.heat + (i - nf), v);
                 else tally_add(S.rad + (i - nf - nh), v);
-                ++n_tal;
+                CNT_ADD(CNT_TALLY, 1u);
             }
         }
     }
@@ -1484,9 +1568,6 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         unsigned long long v = n_cell;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
         if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(S.stats) + 1, v);
-        v = n_tal;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-        if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(S.stats) + 7, v);
         double a = sm.acc_atm[threadIdx.x];
         for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(FULL, a, o);
         if (lane == 0) atomicAdd(&S.stats->w_atm, a);
@@ -1525,20 +1606,23 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 
 typedef void (*transport_fn)(const DevScene);
 template <int NP>
-static transport_fn pick_transport_np(bool pl, bool fz, bool cam) {
+static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz) {
     // CAM (all-sky camera sensors present) is its own specialisation: the camera's local estimate is a large cold path
-    // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false)
-    if (cam) return pl ? transport_kernel<true, false, NP, true> : transport_kernel<false, false, NP, true>;
-    if (pl) return fz ? transport_kernel<true, true, NP, false> : transport_kernel<true, false, NP, false>;
-    return fz ? transport_kernel<false, true, NP, false> : transport_kernel<false, false, NP, false>;
+    // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false).
+    // UZ only matters to the kernels that do not tally every level (the per-level ones use single-layer cells).
+    if (pl) {
+        if (cam) return transport_kernel<true, false, NP, true, false>;
+        return fz ? transport_kernel<true, true, NP, false, false> : transport_kernel<true, false, NP, false, false>;
+    }
+    if (cam) return uz ? transport_kernel<false, false, NP, true, true> : transport_kernel<false, false, NP, true, false>;
+    if (fz) return uz ? transport_kernel<false, true, NP, false, true> : transport_kernel<false, true, NP, false, false>;
+    return uz ? transport_kernel<false, false, NP, false, true> : transport_kernel<false, false, NP, false, false>;
 }
-static transport_fn pick_transport(bool pl, bool fz, bool cam, int np) {
+static transport_fn pick_transport(bool pl, bool fz, bool cam, bool uz, int np) {
     switch (np) {
-        case 32: return pick_transport_np<32>(pl, fz, cam);
-        case 64: return pick_transport_np<64>(pl, fz, cam);
-        case 80: return pick_transport_np<80>(pl, fz, cam);
-        case 128: return pick_transport_np<128>(pl, fz, cam);
-        default: return pick_transport_np<96>(pl, fz, cam);
+        case 64: return pick_transport_np<64>(pl, fz, cam, uz);
+        case 128: return pick_transport_np<128>(pl, fz, cam, uz);
+        default: return pick_transport_np<96>(pl, fz, cam, uz);
     }
 }
 
@@ -1591,7 +1675,7 @@ struct Handle {
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3, runcode;
     DevBuf st_e, st_o, st_a, st_b, f2c;
-    DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, sfc_type, sfc_param;
+    DevBuf ext3tot, prop3, ext3, maj, tu3, pmu, pp, pcdf, pgs, pge, sfc_type, sfc_param;
     DevBuf jobs, job_abs, job_cabs, job_fscale, counter, stats, flag;
     DevBuf flux, rad, heat;
     size_t nflux = 0, nrad = 0, nheat = 0;
@@ -1717,7 +1801,7 @@ int b200rt_destroy(void* handle) {
     cudaSetDevice(H->device);
     DevBuf* all[] = {&H->zgrd, &H->e1tot, &H->e1cum, &H->e1, &H->o1, &H->a1, &H->slab_lay0, &H->slab_cz, &H->slab_maj1d,
                      &H->st_e, &H->st_o, &H->st_a, &H->st_b, &H->f2c, &H->slab_cg, &H->group_lo, &H->group_cz, &H->group_maj1d, &H->gz_lo, &H->empty3, &H->runcode,
-                     &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->sfc_type,
+                     &H->ext3tot, &H->prop3, &H->ext3, &H->maj, &H->tu3, &H->pmu, &H->pp, &H->pcdf, &H->pgs, &H->pge, &H->sfc_type,
                      &H->sfc_param, &H->jobs, &H->job_abs, &H->job_cabs, &H->job_fscale, &H->counter, &H->stats, &H->flag,
                      &H->flux, &H->rad, &H->heat};
     for (DevBuf* b : all) b->release();
@@ -1783,7 +1867,14 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.shard_rank = opt->shard_rank; S.shard_world = opt->shard_world;
 
     // ------------------------------------------------ super-voxel grid
-    const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0;
+    // Tiny radiance tallies (1 x 1-pixel views of plane-parallel / few-column scenes, the columns of an IPA look-up
+    // table) are kept block-private in shared memory, which only the per-level kernels do: such scenes take that route
+    size_t rad_doubles = 0;
+    if ((opt->target & B200RT_TARGET_RADIANCE) && sc->sensors)
+        for (int k = 0; k < sc->nrad; ++k) rad_doubles += size_t(std::max(0, sc->sensors[k].nxr)) * size_t(std::max(0, sc->sensors[k].nyr));
+    rad_doubles *= size_t(opt->nslab);
+    const bool tiny_rad = opt->smem_tally >= 0 && rad_doubles > 0 && rad_doubles <= 512 && (nz3 <= 0 || size_t(sc->nx) * sc->ny <= 64);
+    const bool per_level = (opt->target & (B200RT_TARGET_FLUX | B200RT_TARGET_HEATING)) != 0 || tiny_rad;
     // auto sizes: fine cells of 2 x 2 columns and as many layers as make them 0.6 x as high as wide; coarse (empty-space)
     // cells of 4 x 4 fine cells horizontally and about the same physical height (tuned on the config-2 scene,
     // tools/sweep_sv.py; any choice is unbiased, tests/test_gpu_parity.py sweeps several)
@@ -2022,9 +2113,33 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
             }
             fc[size_t(t) * na + na - 1] = 1.0f;
         }
-        if ((rc = upload(H, H->pmu, fmu)) || (rc = upload(H, H->pp, fp)) || (rc = upload(H, H->pcdf, fc))) return rc;
+        // guide tables (built from the float32 values the kernel compares against)
+        if (na > 65535) return fail(H, B200RT_ERR_ARG, "phase table: at most 65535 angles");
+        std::vector<unsigned short> gs(size_t(sc->npf) * RT_NGS), ge(RT_NGE);
+        for (int t = 0; t < sc->npf; ++t) {
+            const float* F = fc.data() + size_t(t) * na;
+            int j = 0;
+            for (int k = 0; k < RT_NGS; ++k) {
+                const float x = float(k) / float(RT_NGS);
+                while (j + 1 <= na - 2 && F[j + 1] <= x) ++j;
+                gs[size_t(t) * RT_NGS + k] = (unsigned short)j;
+            }
+        }
+        {
+            int j = 0;
+            for (int k = 0; k < RT_NGE; ++k) {
+                const double q = double(k) * (2.0 / RT_NGE);                 // start of bin k: every mu of the bin is <= 1 - q^2 / 2
+                const double muk = 1.0 - 0.5 * q * q;
+                while (j + 1 <= na - 2 && double(fmu[j + 1]) >= muk) ++j;
+                ge[k] = (unsigned short)std::max(0, j - 1);                  // one interval of slack for the rounding of q
+            }
+        }
+        if ((rc = upload(H, H->pmu, fmu)) || (rc = upload(H, H->pp, fp)) || (rc = upload(H, H->pcdf, fc)) || (rc = upload(H, H->pgs, gs)) ||
+            (rc = upload(H, H->pge, ge)))
+            return rc;
         S.pt.npf = sc->npf; S.pt.nang = na;
         S.pt.mu = (const float*)H->pmu.p; S.pt.p = (const float*)H->pp.p; S.pt.cdf = (const float*)H->pcdf.p;
+        S.pt.gs = (const unsigned short*)H->pgs.p; S.pt.ge = (const unsigned short*)H->pge.p;
     }
 
     // ------------------------------------------------ surface
@@ -2123,10 +2238,14 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     // (smem_tally: < 0 off; 0 auto = one copy per block, warp-aggregated shared atomics; 2 = one copy per warp when that
     // fits 24 KB, plain read-modify-write after the aggregation)
     S.ntal_flux_smem = 0; S.ntal_heat_smem = 0; S.ntal_rad_smem = 0; S.tal_per_warp = 0;
-    if (opt->smem_tally >= 0) {
-        size_t budget = 2048;
-        if (per_level && H->nflux + H->nheat <= budget) { S.ntal_flux_smem = int(H->nflux); S.ntal_heat_smem = int(H->nheat); budget -= H->nflux + H->nheat; }
-        if (H->nrad > 0 && H->nrad <= std::min<size_t>(budget, 512)) S.ntal_rad_smem = int(H->nrad);
+    if (opt->smem_tally >= 0 && per_level) {
+        // two blocks per SM must still fit (pools of 96 slots per warp + tables + accumulators + the private tallies)
+        auto fits2 = [&](size_t ntal) {
+            const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(RT_TPB) * 8 + size_t(RT_TPB / 32) * size_t(POOL_WORDS(96)) * 4 + 8 * ntal;
+            return 2 * (smem + 1024) <= size_t(227) * 1024;
+        };
+        if (H->nflux + H->nheat <= 2048 && fits2(H->nflux + H->nheat)) { S.ntal_flux_smem = int(H->nflux); S.ntal_heat_smem = int(H->nheat); }
+        if (H->nrad > 0 && H->nrad <= 512 && fits2(size_t(S.ntal_flux_smem) + S.ntal_heat_smem + H->nrad)) S.ntal_rad_smem = int(H->nrad);
         const size_t tot = size_t(S.ntal_flux_smem) + S.ntal_heat_smem + S.ntal_rad_smem;
         if (opt->smem_tally == 2 && tot > 0 && tot * 8 * (RT_TPB / 32) <= 24 * 1024) S.tal_per_warp = 1;
     }
@@ -2134,9 +2253,9 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     H->k_cam = false;
     for (int k = 0; k < sc->nrad; ++k) if (sc->sensors[k].kind == 1) H->k_cam = true;
     H->pool_slots = opt->pool_slots;
-    if (H->pool_slots != 0 && H->pool_slots != 32 && H->pool_slots != 64 && H->pool_slots != 80 && H->pool_slots != 96 && H->pool_slots != 128 &&
+    if (H->pool_slots != 0 && H->pool_slots != 64 && H->pool_slots != 96 && H->pool_slots != 128 &&
         H->pool_slots != 1024 && H->pool_slots != 1536 && H->pool_slots != 2048)
-        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 1024, 1536 or 2048 (per block) or 32 ... 128 (per warp, v8 kernel)");
+        return fail(H, B200RT_ERR_ARG, "pool_slots must be 0 (auto), 64, 96 or 128 (per warp) -- or 1024, 1536, 2048 per block in builds with the role-specialised experiment");
     H->opt = *opt;
     H->have_scene = true;
     H->ran = false;
@@ -2259,7 +2378,8 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     {
     const int np = H->pool_slots > 0 && H->pool_slots <= 128 ? H->pool_slots : 96;
     int bps = 0;
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, np);
+    // UZ kernels: equally thick 3-D layers with runs (S.uz_ok) -- or no 3-D block at all (the layer search is dead code then)
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, S.uz_ok != 0 || S.nz3 <= 0, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");

@@ -73,7 +73,13 @@ struct PhaseTab {
     const float* mu;    // [nang]        cos(scattering angle), DEcreasing (angle increasing)
     const float* p;     // [npf][nang]   normalised phase function, piecewise linear in mu
     const float* cdf;   // [npf][nang]   F[j] = Prob(angle <= ang[j]) ; F[0] = 0, F[nang-1] = 1
+    // O(1) guide tables (accelerators only: the interval found is the one a full search finds, see tab_*1)
+    const unsigned short* gs;   // [npf][RT_NGS]  sampling: largest j with F[j] <= k / RT_NGS
+    const unsigned short* ge;   // [RT_NGE]       evaluation: an index at or before the interval of any mu whose
+                                //                q = sqrt(2 - 2 mu) falls into bin k (bins uniform in q ~ angle)
 };
+#define RT_NGS 2048
+#define RT_NGE 2048
 
 __device__ __forceinline__ float hg_eval(float g, float mu) {
     const float d = 1.0f + g * g - 2.0f * g * mu;
@@ -92,18 +98,23 @@ __device__ __forceinline__ float ray_sample(float xi) {
     return fminf(1.0f, fmaxf(-1.0f, q - 1.0f / q));
 }
 
+// Tabulated phase functions.  MCARaTS looks its tables up in O(1) (Sca_ntg = 20000 equal-probability bins,
+// er3t/rtm/mca/mca_inp.py:53); here a guide table gives the neighbourhood and a short scan finds the EXACT interval of
+// the caller's angle grid (largest lo with m[lo] >= mu, resp. F[lo] <= xi -- what a binary search over the whole table
+// returns), so the piecewise-linear function that is sampled and evaluated does not depend on the guide resolution.
+// Expected scan length < 1 step on the 498-angle Mie grid (9 dependent loads for the binary search it replaces).
 __device__ __noinline__ float tab_eval1(const PhaseTab& T, int it, float mu) {
     const float* m = T.mu;
     const int n = T.nang;
     if (mu >= __ldg(m)) return __ldg(T.p + size_t(it) * n);
     if (mu <= __ldg(m + n - 1)) return __ldg(T.p + size_t(it) * n + n - 1);
-    int lo = 0, hi = n - 1;                 // m[lo] >= mu > m[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(m + mid) >= mu) lo = mid; else hi = mid;
-    }
-    const float m0 = __ldg(m + lo), m1 = __ldg(m + hi);
-    const float p0 = __ldg(T.p + size_t(it) * n + lo), p1 = __ldg(T.p + size_t(it) * n + hi);
+    const float q = sqrtf(fmaxf(0.0f, 2.0f - 2.0f * mu));
+    int lo = int(__ldg(T.ge + min(RT_NGE - 1, int(q * (0.5f * RT_NGE)))));
+    float m0 = __ldg(m + lo);
+    while (lo > 0 && m0 < mu) { --lo; m0 = __ldg(m + lo); }              // guard (rounding of q); normally not taken
+    float m1 = __ldg(m + lo + 1);
+    while (lo + 1 < n - 1 && m1 >= mu) { ++lo; m0 = m1; m1 = __ldg(m + lo + 1); }
+    const float p0 = __ldg(T.p + size_t(it) * n + lo), p1 = __ldg(T.p + size_t(it) * n + lo + 1);
     const float f = (m0 - mu) / (m0 - m1);
     return p0 + f * (p1 - p0);
 }
@@ -111,15 +122,16 @@ __device__ __noinline__ float tab_eval1(const PhaseTab& T, int it, float mu) {
 __device__ __noinline__ float tab_sample1(const PhaseTab& T, int it, float xi) {
     const int n = T.nang;
     const float* F = T.cdf + size_t(it) * n;
-    int lo = 0, hi = n - 1;                 // F[lo] <= xi < F[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(F + mid) <= xi) lo = mid; else hi = mid;
-    }
+    int lo = int(__ldg(T.gs + size_t(it) * RT_NGS + min(RT_NGS - 1, int(xi * float(RT_NGS)))));
+    float F0 = __ldg(F + lo);
+    while (lo > 0 && F0 > xi) { --lo; F0 = __ldg(F + lo); }              // guard; normally not taken
+    float F1 = __ldg(F + lo + 1);
+    while (lo + 1 < n - 1 && F1 <= xi) { ++lo; F0 = F1; F1 = __ldg(F + lo + 1); }
+    const int hi = lo + 1;
     const float m0 = __ldg(T.mu + lo), m1 = __ldg(T.mu + hi);
     const float p0 = __ldg(T.p + size_t(it) * n + lo), p1 = __ldg(T.p + size_t(it) * n + hi);
     const float dm = m0 - m1;
-    const float c = 2.0f * (xi - __ldg(F + lo));
+    const float c = 2.0f * (xi - F0);
     const float s = (p1 - p0) / dm;
     const float disc = fmaxf(0.0f, p0 * p0 + 2.0f * s * c);
     const float den = p0 + sqrtf(disc);

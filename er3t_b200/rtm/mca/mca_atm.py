@@ -212,14 +212,24 @@ class mca_atm_3d:
         self._fill_nml(cld, nz3, iz3l, atm_tmp, atm_abs, atm_ext, atm_omg, atm_apf)
 
     def _pre_device(self, cld, atm, lay_index, ext_in, nx, ny, nz3, iz3l):
-        """device_props: only extinction and effective radius are touched on the host (two float32 copies into
-        page-locked memory); omega / apf / temperature deviation are lazy."""
+        """device_props: only extinction and effective radius are touched on the host (views of the cloud object's own
+        arrays when those are float32 and C-ordered, else one float32 copy each into page-locked memory); omega / apf /
+        temperature deviation are lazy."""
         cer = cld['cer']['data']
         cer = cer.data if isinstance(cer, np.ma.MaskedArray) else np.asarray(cer)
-        atm_ext = host_zeros((nx, ny, nz3, 1), np.float32)
-        atm_ext[..., 0] = ext_in[:, :, :nz3]
-        cer3 = host_zeros((nx, ny, nz3, 1), np.float32)
-        cer3[..., 0] = cer[:, :, :nz3]
+
+        def as_field(a):
+            # ZERO-COPY when the cloud object already holds float32 C-ordered (nx, ny, nz3) data: the solver then reads
+            # the caller's buffer directly (at full PCIe speed when that buffer is page-locked, e.g.
+            # er3t_b200.util.host_zeros / pin_array); anything else is converted once into page-locked memory
+            v = a[:, :, :nz3]
+            if v.dtype == np.float32 and v.flags['C_CONTIGUOUS'] and v.shape == (nx, ny, nz3):
+                return v.reshape(nx, ny, nz3, 1)
+            out = host_zeros((nx, ny, nz3, 1), np.float32)
+            out[..., 0] = v
+            return out
+        atm_ext = as_field(ext_in)
+        cer3 = as_field(cer)
         self.cer3d = cer3
         ref = np.ascontiguousarray(self.pha.data['ref']['data'], dtype=np.float64)
         ssa = np.ascontiguousarray(self.pha.data['ssa']['data'], dtype=np.float64)

@@ -8,7 +8,7 @@ import datetime
 import numpy as np
 
 __all__ = ['cal_sol_fac', 'cal_mol_ext', 'cal_mol_ext_0', 'g0_calc', 'g_alt_calc', 'get_lay_index', 'nice_array_str',
-           'cal_r_twostream', 'cal_t_twostream', 'cal_ext', 'add_reference', 'print_reference', 'host_zeros']
+           'cal_r_twostream', 'cal_t_twostream', 'cal_ext', 'add_reference', 'print_reference', 'host_zeros', 'pin_array']
 
 _references = []
 
@@ -128,6 +128,23 @@ def host_zeros(shape, dtype=np.float32):
     except Exception:
         pass
     return np.zeros(shape, dtype=dtype)
+
+
+def pin_array(a):
+    """Copy of `a` in page-locked host memory (same dtype, C order) when a CUDA device is present, else `a` made
+    C-contiguous.  For inputs that are uploaded repeatedly (cloud fields of a scene that is re-run): cudaMemcpy from
+    page-locked memory runs at PCIe speed, from pageable memory at roughly a third of it."""
+    a = np.ascontiguousarray(a)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+            out = t.numpy()
+            out[...] = a
+            return out
+    except Exception:
+        pass
+    return a
 
 
 def default_date():

@@ -154,8 +154,8 @@ typedef struct b200rt_options {
     int32_t event_min;            /* lanes parked at an event that end a flight phase early; 0 = auto */
     int32_t empty_runs;           /* vertical merging of empty coarse cells into one box: 0 = auto (on when the 3-D
                                      layers are equally thick and no per-level tally is asked for), -1 = off        */
-    int32_t pool_slots;           /* photon slots in shared memory: per block 1024, 1536, 2048 (kernel 9) or per warp 32, 64,
-                                     80, 96, 128 (kernel 8); 0 = auto */
+    int32_t pool_slots;           /* photon slots in shared memory per warp: 64, 96 or 128; 0 = auto (96).  (1024, 1536, 2048
+                                     per block: only in builds with the role-specialised experiment, kernel 9) */
     int32_t iso_ss;               /* Pho_iso_SS: partial-3D switches to 1-D after this order   */
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */
     int32_t threads_per_block;    /* 0 = auto                                                  */

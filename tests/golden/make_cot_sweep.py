@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""
+Generate tests/golden/ad_cot_sweep.npz: nadir reflectance against cloud optical thickness for the reference's own
+benchmark geometry (examples/00_er3t_bmk.py:24-46,470-579 -- there MCARaTS is compared with libRadtran/DISORT through
+er3t.rtm.mca.func_ref_vs_cot, er3t/rtm/mca/util.py:105-195): 650 nm, SZA 28.2797 deg, nadir view, Lambertian albedo 0.03,
+water cloud r_eff = 10 um in 1-2 km, the benchmark's 35 COT values 0 ... 400.  Solved here by the DETERMINISTIC
+adding-doubling code (oracle/adding_doubling.py::solve_beam; nadir view => azimuthal mode 0 only) on exactly the 1-D
+inputs the GPU path gets from mca_atm_1d (Rayleigh extinction of the US-76 atmosphere, two-g synthetic gas absorption
+so that the g weighting of mca_out_ng is part of the comparison) and the repo's own 498-angle Mie table.
+
+    python tests/golden/make_cot_sweep.py [--nstreams 120,160,240]       # ~40 min on 8 cores; resolutions are cached
+
+The curve is solved at three quadrature resolutions; `ref` is their Richardson extrapolation in 1 / nstream (order fitted
+from the data), `ref_conv` its distance from the finest solution, `ref_n<k>` the raw curves.
+"""
+import argparse
+import datetime
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
+sys.path.insert(0, ROOT)
+
+from oracle import adding_doubling as ad                      # noqa: E402
+import er3t_b200.pre as bpre                                   # noqa: E402
+from er3t_b200.rtm.mca import mca_atm_1d                       # noqa: E402
+from er3t_b200.rtm.mca.mca_out import cal_factors             # noqa: E402
+
+SZA, ALBEDO, CER = 28.2797, 0.03, 10.0
+COT = np.concatenate((np.arange(0.0, 2.0, 0.5), np.arange(2.0, 30.0, 2.0), np.arange(30.0, 60.0, 5.0), np.arange(60.0, 100.0, 10.0),
+                      np.arange(100.0, 401.0, 50.0)))
+DATE = datetime.datetime(2014, 9, 11)
+
+
+def inputs():
+    """The objects the GPU test hands to func_ref_vs_cot (shared with tests/test_gpu_configs.py through this module)."""
+    atm0 = bpre.atm_atmmod(levels=np.linspace(0.0, 20.0, 21))
+    p = atm0.lev['pressure']['data']
+    frac = (p[:-1] - p[1:]) / (p[0] - p[-1])
+    abs0 = bpre.abs_gen(650.0, frac[:, None] * np.array([0.01, 0.3])[None, :], np.array([0.7, 0.3]), solar=np.array([1.6, 1.6]))
+    pha0 = bpre.pha_mie_wc(wavelength=650.0, reff=[5.0, 10.0, 15.0], nr=96)
+    return atm0, abs0, pha0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--nstreams', default='120,160,240', help='quadrature resolutions; results are cached in the output file')
+    ap.add_argument('--out', default=os.path.join(HERE, 'ad_cot_sweep.npz'))
+    a = ap.parse_args()
+    nstreams = [int(v) for v in a.nstreams.split(',')]
+    atm0, abs0, pha0 = inputs()
+    a1 = mca_atm_1d(atm_obj=atm0, abs_obj=abs0)
+    z = np.asarray(a1.nml[0]['Atm_zgrd0']['data'], dtype=np.float64)
+    nz = z.size - 1
+    ext_ray = np.asarray(a1.nml[0]['Atm_ext1d(1:, 1)']['data'], dtype=np.float64).reshape(-1)[:nz]
+    iref = int(np.argmin(np.abs(pha0.data['ref']['data'] - CER)))
+    pcloud = ad.table(pha0.data['ang']['data'], pha0.data['pha']['data'][:, iref])
+    ssa = float(pha0.data['ssa']['data'][iref])
+    pr = ad.rayleigh()
+    icl = [i for i in range(nz) if z[i] >= 1000.0 - 1e-6 and z[i + 1] <= 2000.0 + 1e-6]
+    Ng = abs0.Ng
+    f_rad, toa = cal_factors(DATE, abs0, 1, Ng)
+    f_rad = np.asarray(f_rad, dtype=np.float64)[0]
+    mu0 = np.cos(np.deg2rad(SZA))
+    have = {}
+    if os.path.isfile(a.out):
+        old = np.load(a.out)
+        have = {k: old[k] for k in old.files if k.startswith('ref_n')}
+    for ns in nstreams:
+        key = 'ref_n%d' % ns
+        if key in have:
+            continue
+        ref = np.zeros(COT.size)
+        t0 = time.time()
+        for ic, cot in enumerate(COT):
+            rad = 0.0
+            for ig in range(Ng):
+                absg = np.asarray(a1.nml[ig]['Atm_abs1d(1:, 1)']['data'], dtype=np.float64).reshape(-1)[:nz]
+                layers = []
+                for iz in range(nz - 1, -1, -1):
+                    dz = float(z[iz + 1] - z[iz])
+                    ec = cot / len(icl) / dz if iz in icl else 0.0
+                    layers.append(dict(dz=dz, comps=[(ext_ray[iz], 1.0, pr), (ec, ssa, pcloud)], absorb=absg[iz]))
+                r = ad.solve_beam(layers, ALBEDO, SZA, nstream=ns, views=[(0.0, 0.0)], nmode=1)
+                rad += f_rad[ig] * r['rad_views'][0]
+            ref[ic] = np.pi * rad / (toa * mu0)
+            print('nstream %d  COT %6.1f  ref %.6f  (%.0f s)' % (ns, cot, ref[ic], time.time() - t0), flush=True)
+        have[key] = ref
+        np.savez_compressed(a.out, cot=COT, sza=SZA, albedo=ALBEDO, cer=CER, ext_ray=ext_ray, z=z, **have)
+    # Richardson extrapolation in 1 / nstream from the three finest resolutions: ref(n) = ref_inf + c n^-p
+    ns = sorted(int(k[5:]) for k in have)
+    out = dict(cot=COT, sza=SZA, albedo=ALBEDO, cer=CER, ext_ray=ext_ray, z=z, **have)
+    if len(ns) >= 3:
+        n1, n2, n3 = ns[-3:]
+        r1, r2, r3 = have['ref_n%d' % n1], have['ref_n%d' % n2], have['ref_n%d' % n3]
+        # order p from the ratio of successive differences (median over the cloudy COTs), solved by bisection
+        ratio = np.median(((r1 - r2) / (r2 - r3))[COT >= 2.0])
+        lo, hi = 0.2, 12.0
+        for _ in range(80):
+            p = 0.5 * (lo + hi)
+            val = (n1 ** -p - n2 ** -p) / (n2 ** -p - n3 ** -p)
+            lo, hi = (p, hi) if val < ratio else (lo, p)
+        c = (r2 - r3) / (n2 ** -p - n3 ** -p)
+        ref = r3 - c * n3 ** -p
+        out.update(ref=ref, ref_conv=np.abs(ref - r3), order=p, nstream=n3)
+        print('order %.2f; extrapolation moves the finest result by at most %.2e relative' % (p, np.max(np.abs(ref - r3) / np.maximum(r3, 1e-9))))
+    else:
+        n2, n3 = ns[-2:]
+        out.update(ref=have['ref_n%d' % n3], ref_conv=np.abs(have['ref_n%d' % n3] - have['ref_n%d' % n2]), order=0.0, nstream=n3)
+    np.savez_compressed(a.out, **out)
+    print('wrote', a.out)
+
+
+if __name__ == '__main__':
+    main()

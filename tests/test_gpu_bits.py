@@ -44,6 +44,44 @@ def test_phase_functions_match_oracle(solver):
             assert np.max(np.abs(gots - refs)) < 2e-4, apf
 
 
+def test_phase_tables_on_the_498_angle_mie_grid(solver):
+    """The O(1) guide tables must find the SAME interval a full search finds, also on the reference's forward-dense
+    default grid (er3t/pre/pha/pha_mie.py:106-113: 0.01 deg steps below 2 deg, where float32 cosines coincide)."""
+    from er3t_b200.pre.pha import mie_angles_default
+    ang = mie_angles_default()
+    mu_t = np.cos(np.deg2rad(ang))
+    tabs = []
+    for g in (0.86, 0.8):
+        # forward peak (diffraction-like) + broad HG + a rainbow bump + backscatter rise
+        hg = lambda gg: (1 - gg * gg) / (1 + gg * gg - 2 * gg * mu_t) ** 1.5
+        tabs.append(0.45 * hg(0.995) + 0.5 * hg(g) + 0.04 * np.exp(-0.5 * ((ang - 140.0) / 3.0) ** 2) + 0.01 * hg(-0.6))
+    sc = abi.HostScene(np.array([0.0, 1000.0]), [[1e-6]], [[1.0]], [[0.0]], ang=ang, pha=np.stack(tabs, axis=1))
+    solver.upload_scene(sc, abi.make_options(target=abi.TARGET_FLUX, nslab=1))
+    lib = oracle.load()
+    rng = np.random.default_rng(11)
+    # evaluation: uniform in mu, dense in the forward peak, and exactly ON the grid points
+    mu = np.concatenate([np.linspace(-1.0, 1.0, 4001), np.cos(np.deg2rad(rng.uniform(0.0, 3.0, 3000))), mu_t, 0.5 * (mu_t[1:] + mu_t[:-1])])
+    xi = np.concatenate([(np.arange(20000) + 0.5) / 20000, rng.uniform(0.0, 1e-3, 2000), 1.0 - rng.uniform(0.0, 1e-3, 2000)])
+    xi = np.sort(xi)
+    for apf in (1.0, 2.0):
+        ref = np.zeros_like(mu)
+        lib.oracle_phase_eval(C.addressof(sc.struct), apf, mu.ctypes.data, ref.ctypes.data, mu.size)
+        got = solver.phase_eval(apf, mu)
+        # float32 cosines resolve the forward peak only to ~0.02 deg: compare where the table is smooth at that scale,
+        # and bound the peak region by the table's own range
+        smooth = mu < np.cos(np.deg2rad(1.0))
+        assert np.allclose(got[smooth], ref[smooth], rtol=2e-3, atol=1e-5), apf
+        assert np.all(got[~smooth] <= 1.0001 * ref.max()) and np.all(got[~smooth] >= 0.999 * ref[~smooth].min()), apf
+        gots = solver.phase_sample(apf, xi)
+        # device CDF runs from the forward direction, the oracle's from the backward one (see above)
+        refs1 = np.zeros_like(xi)
+        x1 = np.ascontiguousarray(1.0 - xi)
+        lib.oracle_phase_sample(C.addressof(sc.struct), apf, x1.ctypes.data, refs1.ctypes.data, xi.size)
+        assert np.max(np.abs(np.arccos(np.clip(gots, -1, 1)) - np.arccos(np.clip(refs1, -1, 1)))) < np.deg2rad(0.05), apf
+        # sampling is monotone in xi (a wrong interval from the guide table would break this)
+        assert np.all(np.diff(gots) <= 1e-6), apf
+
+
 def test_brdf_matches_oracle(solver):
     lib = oracle.load()
     rng = np.random.default_rng(3)

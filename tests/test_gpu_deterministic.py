@@ -77,3 +77,35 @@ def test_homogeneous_3d_block_1e9_photons_against_adding_doubling(solver, name, 
     flux, rad, st = run_case(solver, fx, 1.0e9, hom3d=True)
     w = check(fx, flux, rad, rtol_nadir)
     print('\n%s hom-3D: %.0f M photons/s; worst relative deviations %s' % (name, st['photons'] / st['elapsed_ms'] / 1e3, w))
+
+
+def test_reflectance_vs_cot_benchmark_against_adding_doubling(solver):
+    """The reference's own benchmark (examples/00_er3t_bmk.py:24-46,470-579: func_ref_vs_cot over 35 COT values 0 ... 400 at
+    650 nm, SZA 28.2797 deg, nadir, albedo 0.03, r_eff 10 um cloud in 1-2 km; there MCARaTS against libRadtran) through this
+    repo's func_ref_vs_cot -- all 35 columns in ONE IPA launch with the tabulated Mie function -- against the deterministic
+    adding-doubling curve of tests/golden/ad_cot_sweep.npz (made by tests/golden/make_cot_sweep.py from the same 1-D
+    inputs) and, as the reference's class does, beside the two-stream estimate cal_r_twostream (er3t/util/util.py:1135).
+    Tolerance: 1.5e-3 relative + 3 x the fixture's convergence estimate + 4 standard errors of the GPU run."""
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sys.path.insert(0, gdir)
+    import make_cot_sweep as mk
+    import er3t_b200.rtm.mca as bmca
+    fx = np.load(os.path.join(gdir, 'ad_cot_sweep.npz'))
+    atm0, abs0, pha0 = mk.inputs()
+    nrun = 4
+    f = bmca.func_ref_vs_cot(fx['cot'], cer0=float(fx['cer']), fdir=None, date=mk.DATE, wavelength=650.0, surface_albedo=float(fx['albedo']),
+                             solar_zenith_angle=float(fx['sza']), solar_azimuth_angle=238.9053, sensor_zenith_angle=0.0,
+                             sensor_azimuth_angle=261.9049, cloud_top_height=2.0, cloud_geometrical_thickness=1.0, Nphoton=2e6,
+                             seed=7, solver_obj=solver, atm0=atm0, pha0=pha0, abs0=abs0, Nrun=nrun)
+    ref, sem = f.ref, f.ref_std / np.sqrt(nrun)
+    tol = 1.5e-3 * fx['ref'] + 3.0 * fx['ref_conv'] + 4.0 * sem
+    dev = np.abs(ref - fx['ref'])
+    print('ref vs COT: max |dev| / ref %.2e, max dev / tol %.2f' % (float(np.max(dev / fx['ref'])), float(np.max(dev / tol))))
+    assert np.all(dev <= tol), (ref.tolist(), fx['ref'].tolist(), (dev / tol).tolist())
+    assert np.all(np.diff(ref) > -4.0 * np.hypot(sem[1:], sem[:-1])) and ref[-1] < 1.0        # monotone within the noise
+    # two-stream estimate of the reference's class: same limits, same order of magnitude in between
+    assert np.all(np.diff(f.ref_2s) > 0) and np.max(np.abs(f.ref_2s - ref)) < 0.12
+    st = f.mca.stats
+    assert abs((st['w_toa_up'] + st['w_sfc_abs'] + st['w_atm_abs'] - st['w_roulette']) / st['photons'] - 1.0) < 1e-9

@@ -24,9 +24,10 @@ from er3t_b200.solver import Solver
 from er3t_b200.rtm.mca import mcarats_ng
 
 
-def run_one(sol, kw, reps, pf=1.0, pool=0):
+def run_one(sol, kw, reps, pf=1.0, pool=0, smem_tally=0):
     prep = mcarats_ng(**dict(kw, dry_run=True, photons=kw['photons'] * pf))
     prep.options.pool_slots = pool
+    prep.options.smem_tally = smem_tally
     jobs, keep = abi.make_jobs(**prep.jobs_args)
     t0 = time.time()
     sol.upload_scene(prep.scene, prep.options)
@@ -50,6 +51,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--pool', type=int, default=0, help='photon slots per warp (0 = auto)')
+    ap.add_argument('--smem-tally', type=int, default=0, help='-1 global atomics only, 0 auto, 2 one private copy per warp')
     ap.add_argument('--photon-factor', type=float, default=1.0, help='multiply the photon count only (ncu captures)')
     ap.add_argument('--configs', default='C1,C2,C3,C4,C5')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'configs.json'))
@@ -59,7 +61,7 @@ def main():
     for name in a.configs.split(','):
         built = workloads.build(name, scale=a.scale)
         pairs = built if isinstance(built, list) else [built]
-        parts = [run_one(sol, kw, a.reps, a.photon_factor, a.pool) for kw, _ in pairs]
+        parts = [run_one(sol, kw, a.reps, a.photon_factor, a.pool, a.smem_tally) for kw, _ in pairs]
         kw0 = pairs[0][0]
         n = sum(p['photons'] for p in parts)
         ms = sum(p['kernel_ms'] for p in parts)

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for v in "$@"; do
   export ER3T_B200_LIB=$PWD/tools/variants/lib$v.so
   if [ "$MODE" == "bench" ]; then
-    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/variant_$v.json 2> gpurun_out/variant_$v.err
+    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-accuracy --e2e-steps 1 > gpurun_out/variant_$v.json 2> gpurun_out/variant_$v.err
     python -c "import json; d=json.load(open('gpurun_out/variant_$v.json')); print('$v', round(d['value']/1e6,1), 'M photons/s resident', round(d['e2e']['value']/1e6,1), 'e2e')"
   else
     python tools/bench_configs.py --configs $MODE --reps 2 --out gpurun_out/variant_cfg_$v.json 2>&1 | python -c "

@@ -23,6 +23,18 @@ SEED = 20260101
 DATE = datetime.datetime(2017, 8, 13)
 
 
+_PHA_CACHE = {}
+
+
+def _pha(wavelength, **kw):
+    """pha_mie_wc memoised per process (the Mie table costs seconds and several configs share a wavelength)."""
+    from er3t_b200.pre import pha_mie_wc
+    key = (float(wavelength), tuple(sorted((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in kw.items())))
+    if key not in _PHA_CACHE:
+        _PHA_CACHE[key] = pha_mie_wc(wavelength=wavelength, **kw)
+    return _PHA_CACHE[key]
+
+
 def _round_even(v, lo=4):
     return max(lo, int(round(v / 2.0)) * 2)
 
@@ -32,7 +44,7 @@ def c1(scale=1.0, photons=1e6, hom3d=False):
     from er3t_b200.rtm.mca import mca_atm_1d, mca_atm_3d, mca_sca
     atm0 = atm_atmmod(levels=np.arange(0.0, 20.1, 1.0))
     abs0 = abs_16g(wavelength=650.0, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=650.0, reff=[5.0, 10.0, 15.0, 20.0], nr=64)
+    pha0 = _pha(650.0, reff=[5.0, 10.0, 15.0, 20.0], nr=64)
     atm1d0 = mca_atm_1d(atm_obj=atm0, abs_obj=abs0)
     atm_3ds = []
     if hom3d:
@@ -59,7 +71,7 @@ def c2(scale=1.0, photons=1e8, nx=480, ny=480, nz3=100, nrun=3, parts=False):
     atm0 = atm_atmmod(levels=levels)
     abs0 = abs_16g(wavelength=650.0, atm_obj=atm0)
     cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=0.1, dy=0.1, altitude=0.5 + dz * (np.arange(nz3) + 0.5), seed=2, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=650.0)
+    pha0 = _pha(650.0)
     kw = dict(date=DATE, atm_1ds=[mca_atm_1d(atm_obj=atm0, abs_obj=abs0)],
               atm_3ds=[mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True)], Ng=abs0.Ng, target='radiance',
               surface_albedo=0.03, sca=mca_sca(pha_obj=pha0), solar_zenith_angle=28.9, solar_azimuth_angle=296.83,
@@ -82,7 +94,7 @@ def c3(scale=1.0, photons=1e8, views=((0.0, 0.0), (30.0, 90.0), (60.0, 200.0))):
     abs0 = abs_16g(wavelength=650.0, atm_obj=atm0)
     cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=0.25, dy=0.25, altitude=np.arange(0.75, 4.0, 0.5), cloud_frac=0.4, corr_km=2.5,
                        cot_median=10.0, seed=3, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=650.0)
+    pha0 = _pha(650.0)
     rng = np.random.default_rng(SEED)
     sfc0 = sfc_2d_gen(sfc_2d={'fiso': rng.uniform(0.05, 0.3, (nx, ny)), 'fgeo': rng.uniform(0.0, 0.05, (nx, ny)),
                               'fvol': rng.uniform(0.0, 0.15, (nx, ny))})
@@ -107,7 +119,7 @@ def c4(scale=1.0, photons=1e9, nwvl=8):
     atm0 = atm_atmmod(levels=np.arange(0.0, 20.1, 0.5))
     cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=0.25, dy=0.25, altitude=np.arange(0.75, 3.0, 0.5), cloud_frac=0.3, corr_km=3.0,
                        cot_median=6.0, seed=4, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=770.0)
+    pha0 = _pha(770.0)
     rng = np.random.default_rng(SEED + 4)
     sfc0 = sfc_2d_gen(sfc_2d=rng.uniform(0.1, 0.4, (nx, ny)).astype(np.float32))
     sfc = mca_sfc_2d(atm_obj=atm0, sfc_obj=sfc0, quiet=True)
@@ -142,7 +154,7 @@ def c5(scale=1.0, photons=1e7, segment=0, pha0=None):
     abs0 = abs_16g(wavelength=745.0, atm_obj=atm0, tau_max=1.0)
     cld0 = cld_gen_les(Nx=nx, Ny=ny, dx=2.0, dy=2.0, altitude=np.array([1.5, 2.5, 3.5]), cloud_frac=0.5, corr_km=12.0,
                        cot_median=12.0, seed=5 + 31 * segment, atm_obj=atm0)
-    pha0 = pha_mie_wc(wavelength=745.0) if pha0 is None else pha0
+    pha0 = _pha(745.0) if pha0 is None else pha0
     oc = cal_ocean_brdf(wvl=745.0, u10=np.full((nx, ny), 5.0))
     sfc0 = sfc_2d_gen(sfc_2d=oc)
     kw = dict(date=DATE, atm_1ds=[mca_atm_1d(atm_obj=atm0, abs_obj=abs0)],
@@ -157,7 +169,7 @@ def c5_segments(scale=1.0, photons=1e7, nseg=30):
     """The ~30 flight-track segments of projects/03_spns_flux-sim.py:48-53: one independent scene (own cloud field) and
     one mcarats_ng call per segment, 1e7 photons each.  Returns a LIST of (kw, abs) pairs like c4."""
     from er3t_b200.pre import pha_mie_wc
-    pha0 = pha_mie_wc(wavelength=745.0)
+    pha0 = _pha(745.0)
     return [c5(scale, photons, segment=i, pha0=pha0) for i in range(nseg)]
 
 
