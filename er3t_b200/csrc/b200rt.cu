@@ -709,68 +709,6 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
         tmz = cz ? fminf(T, (zl[lzc] - za) * isz) : tmz;                      \
         IDX = (lzc * S.ny + fy) * S.nx + fx;                                  \
     }
-#ifdef RT_LE_SPLIT
-    // Two independent chains per ray: the 3-D piece [0, T] is cut in the middle and both halves are marched in the same
-    // loop -- two voxel loads in flight per lane instead of one, half the trip count (the march is bound by the latency of
-    // its dependent gathers).  Chain B starts from the POSITION at T / 2; both chains cover their half exactly.
-    const float Tfull = T;
-    const bool split = Tfull * (fabsf(se.s.x) * S.inv_dx + fabsf(se.s.y) * S.inv_dy) + float(S.nz3) * fabsf((ze - za) / (zb1 - zb0)) >= 4.0f;
-    const float tB = 0.5f * Tfull;
-    // chain B state
-    float xB = wrapf(x + se.s.x * tB, S.Lx, S.inv_Lx), yB = wrapf(y + se.s.y * tB, S.Ly, S.inv_Ly);
-    const float zB = za + se.s.z * tB;
-    int fxB = min(S.nx - 1, max(0, int(xB * S.inv_dx))), fyB = min(S.ny - 1, max(0, int(yB * S.inv_dy)));
-    int lzB = lz;
-    while (lzB + dl != lzend && (up ? zB >= zl[lzB] : zB <= zl[lzB])) lzB += dl;
-    float tmxB = se.s.x != 0.0f ? tB + fmaxf(0.0f, (float(fxB + (px ? 1 : 0)) * S.dx - xB) * isx) : RT_INF;
-    float tmyB = se.s.y != 0.0f ? tB + fmaxf(0.0f, (float(fyB + (py ? 1 : 0)) * S.dy - yB) * isy) : RT_INF;
-    float tmzB = fminf(Tfull, (zl[lzB] - za) * isz);
-    float tBcur = tB;
-    // chain A ends where B starts
-    const float TA = split ? tB : Tfull;
-    tmz = fminf(TA, tmz);
-    bool dA = false, dB = !split;
-    float eA = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
-    float eB = split ? __ldg(base + (lzB * S.ny + fyB) * S.nx + fxB) : 0.0f;
-#define LE_STEP2(TM_X, TM_Y, TM_Z, TT, FX, FY, LZ, TEND, SEG, IDX, DONE)      \
-    {                                                                         \
-        const float tn = fminf(fminf(TM_X, TM_Y), TM_Z);                      \
-        SEG = tn - TT;                                                        \
-        TT = tn;                                                              \
-        const bool cx = TM_X <= TM_Y && TM_X <= TM_Z;                         \
-        const bool cy = !cx && TM_Y <= TM_Z;                                  \
-        const bool cz = !(cx || cy);                                          \
-        int nfx = FX + sx, nfy = FY + sy;                                     \
-        nfx = nfx >= S.nx ? 0 : (nfx < 0 ? S.nx - 1 : nfx);                   \
-        nfy = nfy >= S.ny ? 0 : (nfy < 0 ? S.ny - 1 : nfy);                   \
-        FX = cx ? nfx : FX;                                                   \
-        FY = cy ? nfy : FY;                                                   \
-        LZ = cz ? LZ + dl : LZ;                                               \
-        TM_X = cx ? TM_X + tdx : TM_X;                                        \
-        TM_Y = cy ? TM_Y + tdy : TM_Y;                                        \
-        DONE = tn >= TEND || LZ == lzend;                                     \
-        const int lzc = min(S.nz3 - 1, max(0, LZ));                           \
-        TM_Z = cz ? fminf(TEND, (zl[lzc] - za) * isz) : TM_Z;                 \
-        IDX = (lzc * S.ny + FY) * S.nx + FX;                                  \
-    }
-    for (;;) {
-        float segA, segB;
-        int iA, iB;
-        bool nA, nB;
-        LE_STEP2(tmx, tmy, tmz, t, fx, fy, lz, TA, segA, iA, nA);
-        LE_STEP2(tmxB, tmyB, tmzB, tBcur, fxB, fyB, lzB, Tfull, segB, iB, nB);
-        n_visit += (dA ? 0u : 1u) + (dB ? 0u : 1u);
-        segA = dA ? 0.0f : segA; segB = dB ? 0.0f : segB;
-        nA = nA || dA; nB = nB || dB;
-        const float enA = nA ? 0.0f : __ldg(base + iA);
-        const float enB = nB ? 0.0f : __ldg(base + iB);
-        tau3 = fmaf(eA, segA, tau3);
-        tau3 = fmaf(eB, segB, tau3);
-        if (nA && nB) break;
-        eA = enA; eB = enB; dA = nA; dB = nB;
-    }
-#undef LE_STEP2
-#else
     float e = __ldg(base + (lz * S.ny + fy) * S.nx + fx);
     for (;;) {
         float seg;
@@ -782,7 +720,6 @@ __device__ __noinline__ float le_tau_generic(const DevScene& S, const float* __r
         if (done) break;
         e = en;
     }
-#endif
 #undef LE_STEP
     *n_visit_out = n_visit;
     return tau + tau3;
@@ -817,9 +754,6 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
         }
         return fmaxf(0.0f, t1) * se.inv_sz;
     }
-#ifdef RT_NO_GENERIC_LE      /* experiment switch: kernels without the oblique-view march (valid for vertical views only) */
-    return 0.0f;
-#endif
     if (frozen) { fx = p.cix; fy = p.ciy; }
     unsigned nv = 0;
     const RayTarget rt = {se.s, se.zt, se.lt};
@@ -962,9 +896,10 @@ __device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, c
 // only synchronisation is __syncwarp.
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
-// UZ: the 3-D layers are equally thick and vertical runs of empty cells are on (S.uz_ok): the fine slab of a photon that
-//     left a box sideways follows from its height, and the layer search for unequal layers is not part of the flight
-//     loop at all.  Measured on config 2: the ~35 never-executed instructions of that search cost 3.4 % (the loop is
+// UZ (per-level kernels): the tight 1-D layer step is compiled in (plane-parallel and few-column scenes).
+// UZ (other kernels): the 3-D layers are equally thick, vertical runs of empty cells are on (S.uz_ok) and every coarse z cell is one fine
+//     slab: the fine slab of a photon that left a box sideways follows from its height, and the layer search for unequal
+//     layers is not part of the flight loop at all (the other kernels keep both, decided at run time).  Measured on config 2: the ~35 never-executed instructions of that search cost 3.4 % (the loop is
 //     instruction-fetch sensitive, profiles/README.md r02_f), hence a template parameter instead of a run-time test.
 template <bool PL, bool FZ, int NP, bool CAM, bool UZ>
 __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
@@ -1164,12 +1099,74 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const float Lux = S.Lux, Luy = S.Luy;
             const int ncx = S.ncx, ncy = S.ncy;
             const int cmx = (1 << S.shx) - 1, cmy = (1 << S.shy) - 1;
+            const float inv_Lux = 1.0f / Lux, inv_Luy = 1.0f / Luy;
             const float* __restrict__ majp = S.maj;
             int ev = EV_NONE;
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
-                if (have && ev == EV_NONE) {
-                    if (!PL && UZ && (p.flags & FL_STALE)) {
+                bool plane = false;
+                if (PL && UZ && have && ev == EV_NONE) {
+                    // ---- per-level targets: a 1-D layer as its own tight step.  Every level must be tallied, so 1-D layers
+                    //      cannot be merged into one box as in the radiance kernels; what can go is the generic cell step
+                    //      per layer (a flux run spends most of its steps between TOA and the cloud layer): here a layer
+                    //      costs its look-up, the absorption factor and the tallies.  Same physics as the generic step
+                    //      below; the periodic wrap is a floor instead of a face crossing.  One layer per pass of the loop,
+                    //      so that parked lanes still end the phase early (event_min) and lanes stay in lock-step.
+                    const float4 A1 = sm.slabA[p.is];
+                    plane = __float_as_int(A1.w) < 0;
+                }
+                // (The choice is per LANE: which step a photon takes must not depend on the other photons of its warp, or a
+                // trajectory would no longer be reproducible to the bit -- a warp-uniform choice was measured and broke
+                // tests/test_gpu_bits.py::test_every_photon_is_traced_once_and_shards_add_up.  A warp that mixes 1-D and 3-D
+                // lanes therefore pays for both instruction streams, which is why this step is compiled in only for
+                // plane-parallel and few-column scenes -- template flag UZ of the per-level kernels: on config 5, whose
+                // warps mix most of the time, it cost 18-24 %.)
+                if (PL && UZ && plane) {
+                    const float4 A1 = sm.slabA[p.is];
+                    {
+                        const TallyCtx tc = tally_ctx(S, p.job);
+                        const float zf = upz ? A1.y : A1.x;
+                        const float seg = fmaxf(0.0f, (zf - p.z) * kz);
+                        const float M = A1.z;
+                        const bool hit = p.tau < M * seg;
+                        const float dmove = hit ? __fdividef(p.tau, M) : seg;
+                        if (p.flags & FL_ABS) {
+                            const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
+                            ACC_ADD(ACC_ATM, double(p.w) - double(wn));
+                            if (want_heat) heat_add(S, sm, tc, p.is, tally_col_u(S, ux, uy), double(p.w) - double(wn));
+                            p.w = wn;
+                        }
+                        p.leg += dmove;
+                        ux += dux * dmove; uy += duy * dmove;
+                        ux -= Lux * floorf(ux * inv_Lux); uy -= Luy * floorf(uy * inv_Luy);
+                        ux = (ux >= 0.0f && ux < Lux) ? ux : 0.0f; uy = (uy >= 0.0f && uy < Luy) ? uy : 0.0f;
+                        p.tau = fmaxf(0.0f, p.tau - M * dmove);
+                        if (!frozen) {
+                            p.cix = min(ncx - 1, max(0, __float2int_rd(ux)));
+                            p.ciy = min(ncy - 1, max(0, __float2int_rd(uy)));
+                        }
+                        if (hit) {
+                            p.z += dzg * dmove;
+                            ev = EV_TENT;
+                            p.M = M;
+                            p.flags = (p.flags & ~FL_IN3) | FL_EMPTY;
+                        } else {
+                            p.z = zf;
+                            p.flags &= ~FL_STALE;
+                            if (want_flux) {
+                                const int col = tally_col_u(S, ux, uy);
+                                if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tc, 0, p.is, col, p.w);
+                                flux_add(S, sm, tc, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
+                            }
+                            const int nis = upz ? p.is + 1 : p.is - 1;
+                            if (nis >= S.nslab_z) ev = EV_ESC;
+                            else if (nis < 0) ev = EV_SFC;
+                            else p.is = nis;
+                        }
+                    }
+                }
+                if (have && ev == EV_NONE && !plane) {
+                    if (!PL && (UZ || S.uz_ok) && (p.flags & FL_STALE)) {
                         // left a box of several fine slabs sideways: the slab follows from the height
                         p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
                         p.flags &= ~FL_STALE;
@@ -1316,7 +1313,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 RNG4(u);
                 {
                     // layer of the collision point inside the cell the photon parked in (deferred from the flight phase)
-                    const bool by_height = !PL && UZ && ev_empty && ev_in3;     // the box may span several z groups
+                    const bool by_height = !PL && (UZ || S.uz_ok) && ev_empty && ev_in3;     // the box may span several z groups
                     if (by_height) p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
                     const int4 sb = sm.slabB[p.is];
                     int l0 = sb.x, l1 = sb.y;
@@ -1611,8 +1608,10 @@ static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz) {
     // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false).
     // UZ only matters to the kernels that do not tally every level (the per-level ones use single-layer cells).
     if (pl) {
+        // (per-level kernels: the last flag compiles the tight 1-D layer step in -- plane-parallel / few-column scenes)
         if (cam) return transport_kernel<true, false, NP, true, false>;
-        return fz ? transport_kernel<true, true, NP, false, false> : transport_kernel<true, false, NP, false, false>;
+        if (fz) return uz ? transport_kernel<true, true, NP, false, true> : transport_kernel<true, true, NP, false, false>;
+        return uz ? transport_kernel<true, false, NP, false, true> : transport_kernel<true, false, NP, false, false>;
     }
     if (cam) return uz ? transport_kernel<false, false, NP, true, true> : transport_kernel<false, false, NP, true, false>;
     if (fz) return uz ? transport_kernel<false, true, NP, false, true> : transport_kernel<false, true, NP, false, false>;
@@ -1671,6 +1670,7 @@ struct Handle {
     size_t smem_bytes = 0, smem_tables = 0;
     int pool_slots = 0;
     bool k_pl = false, k_fz = false, k_cam = false;
+    int cmz = 1;                 // fine slabs per coarse z cell of the uploaded scene
     // owned device memory
     std::vector<DevBuf*> pool;
     DevBuf zgrd, e1tot, e1cum, e1, o1, a1, slab_lay0, slab_cz, slab_maj1d, slab_cg, group_lo, group_cz, group_maj1d, gz_lo, empty3, runcode;
@@ -1907,6 +1907,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     S.ncx = (sc->nx + svx - 1) / svx; S.ncy = (sc->ny + svy - 1) / svy; S.ncz = nz3 > 0 ? (nz3 + svz - 1) / svz : 0;
     // the z-group tables live in shared memory: at most 128 groups in the 3-D block unless the caller chose cmz
     if (opt->cmz <= 0 && !per_level && S.ncz > 128 * cmz) cmz = (S.ncz + 127) / 128;
+    H->cmz = cmz;
     S.Sx = float(sc->dx * svx); S.Sy = float(sc->dy * svy); S.inv_Sx = 1.0f / S.Sx; S.inv_Sy = 1.0f / S.Sy;
     S.inv_Lx = 1.0f / S.Lx; S.inv_Ly = 1.0f / S.Ly;
     S.Lux = float(double(sc->nx) / svx); S.Luy = float(double(sc->ny) / svy);
@@ -2379,7 +2380,8 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     const int np = H->pool_slots > 0 && H->pool_slots <= 128 ? H->pool_slots : 96;
     int bps = 0;
     // UZ kernels: equally thick 3-D layers with runs (S.uz_ok) -- or no 3-D block at all (the layer search is dead code then)
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, S.uz_ok != 0 || S.nz3 <= 0, np);
+    const bool k_uz = H->k_pl ? (S.nz3 <= 0 || size_t(S.nx) * S.ny <= 64) : ((S.uz_ok != 0 && H->cmz == 1) || S.nz3 <= 0);
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, k_uz, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");

@@ -10,8 +10,8 @@ so that the g weighting of mca_out_ng is part of the comparison) and the repo's 
 
     python tests/golden/make_cot_sweep.py [--nstreams 120,160,240]       # ~40 min on 8 cores; resolutions are cached
 
-The curve is solved at three quadrature resolutions; `ref` is their Richardson extrapolation in 1 / nstream (order fitted
-from the data), `ref_conv` its distance from the finest solution, `ref_n<k>` the raw curves.
+The curve is solved at three quadrature resolutions; `ref` is the finest one, `ref_conv` its distance from the next
+finest (2e-4 relative between 160 and 240 streams), `ref_n<k>` the raw curves.
 """
 import argparse
 import datetime
@@ -91,26 +91,13 @@ def main():
             print('nstream %d  COT %6.1f  ref %.6f  (%.0f s)' % (ns, cot, ref[ic], time.time() - t0), flush=True)
         have[key] = ref
         np.savez_compressed(a.out, cot=COT, sza=SZA, albedo=ALBEDO, cer=CER, ext_ray=ext_ray, z=z, **have)
-    # Richardson extrapolation in 1 / nstream from the three finest resolutions: ref(n) = ref_inf + c n^-p
+    # the finest solution is the fixture; its distance from the next finest one is the convergence estimate (the sequence is
+    # not monotone in nstream -- 120 streams sit 0.3 % low, 160 and 240 agree to 2e-4 -- so no extrapolation is attempted)
     ns = sorted(int(k[5:]) for k in have)
     out = dict(cot=COT, sza=SZA, albedo=ALBEDO, cer=CER, ext_ray=ext_ray, z=z, **have)
-    if len(ns) >= 3:
-        n1, n2, n3 = ns[-3:]
-        r1, r2, r3 = have['ref_n%d' % n1], have['ref_n%d' % n2], have['ref_n%d' % n3]
-        # order p from the ratio of successive differences (median over the cloudy COTs), solved by bisection
-        ratio = np.median(((r1 - r2) / (r2 - r3))[COT >= 2.0])
-        lo, hi = 0.2, 12.0
-        for _ in range(80):
-            p = 0.5 * (lo + hi)
-            val = (n1 ** -p - n2 ** -p) / (n2 ** -p - n3 ** -p)
-            lo, hi = (p, hi) if val < ratio else (lo, p)
-        c = (r2 - r3) / (n2 ** -p - n3 ** -p)
-        ref = r3 - c * n3 ** -p
-        out.update(ref=ref, ref_conv=np.abs(ref - r3), order=p, nstream=n3)
-        print('order %.2f; extrapolation moves the finest result by at most %.2e relative' % (p, np.max(np.abs(ref - r3) / np.maximum(r3, 1e-9))))
-    else:
-        n2, n3 = ns[-2:]
-        out.update(ref=have['ref_n%d' % n3], ref_conv=np.abs(have['ref_n%d' % n3] - have['ref_n%d' % n2]), order=0.0, nstream=n3)
+    n2, n3 = ns[-2:]
+    out.update(ref=have['ref_n%d' % n3], ref_conv=np.abs(have['ref_n%d' % n3] - have['ref_n%d' % n2]), nstream=n3)
+    print('finest %d streams; max relative change against %d streams: %.2e' % (n3, n2, np.max(out['ref_conv'] / out['ref'])))
     np.savez_compressed(a.out, **out)
     print('wrote', a.out)
 

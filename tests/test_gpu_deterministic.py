@@ -85,7 +85,11 @@ def test_reflectance_vs_cot_benchmark_against_adding_doubling(solver):
     repo's func_ref_vs_cot -- all 35 columns in ONE IPA launch with the tabulated Mie function -- against the deterministic
     adding-doubling curve of tests/golden/ad_cot_sweep.npz (made by tests/golden/make_cot_sweep.py from the same 1-D
     inputs) and, as the reference's class does, beside the two-stream estimate cal_r_twostream (er3t/util/util.py:1135).
-    Tolerance: 1.5e-3 relative + 3 x the fixture's convergence estimate + 4 standard errors of the GPU run."""
+
+    The local estimate of a nadir radiance under a Mie phase function has heavy-tailed noise (rare near-forward
+    contributions; profiles/diag_cot_r02_k.txt: 0.1-0.35 % per point at 8e7 photons per COT, no systematic sign), so the
+    test has two parts: every point within 1.5e-3 relative + 3 x the fixture's convergence estimate + 6 standard errors
+    (8 runs), and the MEAN relative deviation over the cloudy points -- where the noise averages down -- within 2.5e-3."""
     import os
     import sys
     gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -94,17 +98,21 @@ def test_reflectance_vs_cot_benchmark_against_adding_doubling(solver):
     import er3t_b200.rtm.mca as bmca
     fx = np.load(os.path.join(gdir, 'ad_cot_sweep.npz'))
     atm0, abs0, pha0 = mk.inputs()
-    nrun = 4
+    nrun = 8
     f = bmca.func_ref_vs_cot(fx['cot'], cer0=float(fx['cer']), fdir=None, date=mk.DATE, wavelength=650.0, surface_albedo=float(fx['albedo']),
                              solar_zenith_angle=float(fx['sza']), solar_azimuth_angle=238.9053, sensor_zenith_angle=0.0,
                              sensor_azimuth_angle=261.9049, cloud_top_height=2.0, cloud_geometrical_thickness=1.0, Nphoton=2e6,
                              seed=7, solver_obj=solver, atm0=atm0, pha0=pha0, abs0=abs0, Nrun=nrun)
     ref, sem = f.ref, f.ref_std / np.sqrt(nrun)
-    tol = 1.5e-3 * fx['ref'] + 3.0 * fx['ref_conv'] + 4.0 * sem
+    tol = 1.5e-3 * fx['ref'] + 3.0 * fx['ref_conv'] + 6.0 * sem
     dev = np.abs(ref - fx['ref'])
-    print('ref vs COT: max |dev| / ref %.2e, max dev / tol %.2f' % (float(np.max(dev / fx['ref'])), float(np.max(dev / tol))))
+    cloudy = fx['cot'] >= 2.0
+    mean_rel = float(np.mean(ref[cloudy] / fx['ref'][cloudy] - 1.0))
+    print('ref vs COT: max |dev| / ref %.2e, max dev / tol %.2f, mean relative deviation (COT >= 2) %+.2e' % (
+        float(np.max(dev / fx['ref'])), float(np.max(dev / tol)), mean_rel))
     assert np.all(dev <= tol), (ref.tolist(), fx['ref'].tolist(), (dev / tol).tolist())
-    assert np.all(np.diff(ref) > -4.0 * np.hypot(sem[1:], sem[:-1])) and ref[-1] < 1.0        # monotone within the noise
+    assert abs(mean_rel) < 2.5e-3, mean_rel
+    assert np.all(np.diff(ref) > -6.0 * np.hypot(sem[1:], sem[:-1])) and ref[-1] < 1.0        # monotone within the noise
     # two-stream estimate of the reference's class: same limits, same order of magnitude in between
     assert np.all(np.diff(f.ref_2s) > 0) and np.max(np.abs(f.ref_2s - ref)) < 0.12
     st = f.mca.stats

@@ -62,3 +62,25 @@ def test_multi_pixel_variant(common):
     assert f.mca.Nx == 4 and f.mca.Ny == 2 and f.ref.shape == (2,) and f.ref[1] > f.ref[0] > 0.0
     # two-stream sanity cross-check, the reference's own loose check (er3t/rtm/mca/util.py:66)
     assert abs(f.ref[1] - f.ref_2s[1]) < 0.15
+
+
+def test_oracle_on_the_reference_benchmark_curve():
+    """Pins the ORACLE on the reference's benchmark geometry (examples/00_er3t_bmk.py:24-46,470-579): reflectance against COT
+    from func_ref_vs_cot with the oracle double against the deterministic adding-doubling curve
+    (tests/golden/ad_cot_sweep.npz); the GPU takes the same test at all 35 COT values and 2e6 photons each
+    (tests/test_gpu_deterministic.py)."""
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sys.path.insert(0, gdir)
+    import make_cot_sweep as mk
+    fx = np.load(os.path.join(gdir, 'ad_cot_sweep.npz'))
+    atm0, abs0, _ = mk.inputs()
+    pha0 = bpre.pha_mie_wc(wavelength=650.0, reff=[5.0, 10.0, 15.0], nr=96)
+    pick = [0, 4, 9, 19, 28]                                  # COT 0, 2, 10, 30, 100
+    nrun = 4
+    f = bmca.func_ref_vs_cot(fx['cot'][pick], cer0=10.0, fdir=None, date=mk.DATE, wavelength=650.0, surface_albedo=float(fx['albedo']),
+                             solar_zenith_angle=float(fx['sza']), Nphoton=6e4, atm0=atm0, seed=21, solver_obj=OracleSolver(), pha0=pha0,
+                             abs0=abs0, Nrun=nrun)
+    sem = f.ref_std / np.sqrt(nrun)
+    dev = np.abs(f.ref - fx['ref'][pick])
+    assert np.all(dev < 4.0 * sem + 3.0 * fx['ref_conv'][pick] + 2e-3 * fx['ref'][pick]), (f.ref, fx['ref'][pick], sem)
