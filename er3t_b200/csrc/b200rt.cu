@@ -1101,6 +1101,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             const int cmx = (1 << S.shx) - 1, cmy = (1 << S.shy) - 1;
             const float inv_Lux = 1.0f / Lux, inv_Luy = 1.0f / Luy;
             const float* __restrict__ majp = S.maj;
+            TallyCtx tcf;                                              // per-level kernels: the photon's tally context, once per visit
+            if (PL && have) tcf = tally_ctx(S, p.job);
             int ev = EV_NONE;
 #pragma unroll 1
             for (int kstep = 0; kstep < S.flight_steps; ++kstep) {
@@ -1124,7 +1126,6 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 if (PL && UZ && plane) {
                     const float4 A1 = sm.slabA[p.is];
                     {
-                        const TallyCtx tc = tally_ctx(S, p.job);
                         const float zf = upz ? A1.y : A1.x;
                         const float seg = fmaxf(0.0f, (zf - p.z) * kz);
                         const float M = A1.z;
@@ -1133,7 +1134,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         if (p.flags & FL_ABS) {
                             const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
                             ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                            if (want_heat) heat_add(S, sm, tc, p.is, tally_col_u(S, ux, uy), double(p.w) - double(wn));
+                            if (want_heat) heat_add(S, sm, tcf, p.is, tally_col_u(S, ux, uy), double(p.w) - double(wn));
                             p.w = wn;
                         }
                         p.leg += dmove;
@@ -1155,8 +1156,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                             p.flags &= ~FL_STALE;
                             if (want_flux) {
                                 const int col = tally_col_u(S, ux, uy);
-                                if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tc, 0, p.is, col, p.w);
-                                flux_add(S, sm, tc, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
+                                if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tcf, 0, p.is, col, p.w);
+                                flux_add(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
                             }
                             const int nis = upz ? p.is + 1 : p.is - 1;
                             if (nis >= S.nslab_z) ev = EV_ESC;
@@ -1218,8 +1219,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
-                            p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
+                            heat_add(S, sm, tcf, p.is, frozen ? p.ciy * S.nx + p.cix : tally_col_u(S, ux, uy), double(p.w) - double(wn));
                         }
                         p.w = wn;
                     }
@@ -1256,12 +1256,9 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     if (zc) {
                         fl &= ~FL_STALE;
                         if (PL && want_flux) {
-                            p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            if (upz) flux_tally(S, sm, p, 2, p.is + 1);
-                            else {
-                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is);
-                                flux_tally(S, sm, p, 1, p.is);
-                            }
+                            const int col = frozen ? p.ciy * S.nx + p.cix : tally_col_u(S, ux, uy);
+                            if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tcf, 0, p.is, col, p.w);
+                            flux_add(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
                         }
                         const int nis = upz ? shi : slo - 1;
                         if (nis >= S.nslab_z) ev = EV_ESC;
