@@ -114,6 +114,46 @@ def test_c5_flux_over_cox_munk_ocean(solver, tmp_path):
     ok, info = _pixels_ok(np.asarray(g['f_down']['data'])[:, :, 0, :], np.asarray(c['f_down']['data'])[:, :, 0, :]); assert ok, info
 
 
+def test_named_variants_against_oracle(solver, tmp_path):
+    """The variants SURVEY.md 8d names beside the five configs, scaled so that the oracle finishes in seconds: C2R (config 2
+    as the reference runs it: 10 layers of 400 m, projects/05_cnn-les_rad-sim.py:92,103), C3V1 (one view per call, what the
+    reference traces: er3t/rtm/mca/mcarats.py:301), C3V9 (nine views 0 ... 60 deg in ONE pass,
+    projects/02_modis_rad-sim.py:66-78), C5S (flight-track segments, one scene each: projects/03_spns_flux-sim.py:48-53)."""
+    # C2R
+    kw, abs0 = workloads.build('C2R', scale=0.004)
+    mg, g, c = _both(kw, abs0, solver, 3e6, 3e5, tmp_path / 'c2r')
+    a, b = np.asarray(g['rad']['data']), np.asarray(c['rad']['data'])
+    ok, info = _mean_ok(a, b, (0, 1)); assert ok, ('C2R', info)
+    ok, info = _pixels_ok(a, b); assert ok, ('C2R', info)
+    # C3V1, C3V9: first sensor through mca_out_ng, the others as extra sensors
+    for name, nextra in (('C3V1', 0), ('C3V9', 8)):
+        kw, abs0 = workloads.build(name, scale=0.003)
+        kw = dict(kw, Nrun=NRUN, fdir=str(tmp_path / name))
+        mg = bmca.mcarats_ng(**dict(kw, photons=2e6, seed=7, solver_obj=solver))
+        mc = bmca.mcarats_ng(**dict(kw, photons=2e5, seed=1007, solver_obj=OracleSolver()))
+        assert abs(_balance(mg.stats)) < 1e-9
+        gg = np.asarray(bmca.mca_out_ng(mca_obj=mg, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data['rad']['data'])
+        cc = np.asarray(bmca.mca_out_ng(mca_obj=mc, abs_obj=abs0, mode='all', squeeze=False, quiet=True).data['rad']['data'])
+        ok, info = _mean_ok(gg, cc, (0, 1)); assert ok, (name, info)
+        ok, info = _pixels_ok(gg, cc); assert ok, (name, info)
+        assert len(mg.rad_extra) == nextra and len(mc.rad_extra) == nextra
+        for k in range(nextra):
+            ok, info = _mean_ok(mg.rad_extra[k], mc.rad_extra[k], (0, 1)); assert ok, (name, k, info)
+            ok, info = _pixels_ok(mg.rad_extra[k], mc.rad_extra[k]); assert ok, (name, k, info)
+        # the nadir view of the nine-view pass sees what the single-view call sees (same seeds, same photons)
+        if name == 'C3V1':
+            nadir_single = gg.mean()
+        else:
+            assert abs(gg.mean() / nadir_single - 1.0) < 0.01
+    # C5S: three of the segments (each its own cloud field)
+    for iseg, (kw, abs0) in enumerate(workloads.build('C5S', scale=0.06, nseg=3)):
+        mg, g, c = _both(kw, abs0, solver, 1e6, 1e5, tmp_path / ('seg%d' % iseg))
+        for key in ('f_up', 'f_down'):
+            a, b = np.asarray(g[key]['data']), np.asarray(c[key]['data'])
+            for lev in (0, -1):
+                ok, info = _mean_ok(a[:, :, lev, :], b[:, :, lev, :], (0, 1)); assert ok, ('C5S', iseg, key, lev, info)
+
+
 def test_c2_named_shape_properties(solver, tmp_path):
     """480 x 480 x 100 voxels (BASELINE.json configs[1]) at a photon count the test budget allows: every photon traced
     exactly once, energy closes to fp64 rounding, radiance finite and positive, cloudy pixels brighter than clear ones."""
