@@ -2,11 +2,14 @@
 //
 // Replaces the external MCARaTS process that er3t launches at er3t/rtm/mca/mca_run.py:110-113,179-181.
 // Kernels (DESIGN.md has the roofline of each):
-//   pack_scene_kernel      per-voxel total extinction + (omega, apf) records        (HBM streaming)
-//   majorant_kernel        super-voxel majorant grid                                (HBM streaming)
+//   pack_scene_tiled_kernel per-voxel total extinction + (omega, apf) records, tiled (ix, k) transpose of the caller's
+//                          C-order fields, (omega, apf) optionally derived from the effective radius  (HBM streaming)
+//   pack_scene_kernel      the same for any other layout / several components / Atm_abst3d           (HBM streaming)
+//   majorant_kernel, empty_kernel, run_kernel, mark_empty_kernel
+//                          fine majorant grid, coarse emptiness, vertical runs of empty cells        (HBM streaming)
 //   tau_up_kernel          optical depth from each voxel to the top of the 3-D block (vertical local estimates)
 //   transport_kernel       persistent-thread photon transport with in-place regeneration, Philox streams,
-//                          super-voxel DDA + null-collision tracking, local-estimate radiance, fp64 tallies
+//                          two-level majorant grid + null-collision tracking, local-estimate radiance, fp64 tallies
 //   check_finite_kernel    NaN/Inf guard over the tallies
 // No CPU fallback exists: every entry point fails with an error code if CUDA fails.
 

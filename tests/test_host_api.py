@@ -168,3 +168,35 @@ def test_hdf5_dump_matches_the_reference_call_for_call(monkeypatch, tmp_path):
     for key, item in o.data.items():
         assert np.array_equal(np.asarray(r.data[key]['data']), np.asarray(item['data']))
         assert r.data[key]['name'] == item['name'] and r.data[key]['units'] == item['units']
+
+
+def test_device_props_hands_over_views_and_lazy_fields_equal_the_host_interpolation():
+    """mca_atm_3d(device_props=True): extinction and effective radius are handed on as VIEWS of the cloud object's own
+    float32 C-ordered arrays (no host copy; other dtypes / layouts are converted once), omega / apf stay available as lazily
+    evaluated arrays that equal what the default path (the restated er3t/rtm/mca/mca_atm.py:291-303) computes, and the scene
+    carries cer3d + the (ref, ssa, asy) tables instead of omg3d / apf3d."""
+    from er3t_b200.util import pin_array
+    atm0 = bpre.atm_atmmod(levels=np.linspace(0, 20, 21))
+    abs0 = bpre.abs_16g(wavelength=650.0, atm_obj=atm0)
+    pha0 = bpre.pha_mie_wc(wavelength=650.0, reff=[5.0, 10.0, 15.0], nr=48)
+    cld0 = bpre.cld_gen_les(Nx=12, Ny=10, dx=0.1, dy=0.1, altitude=np.array([1.5, 2.5]), seed=2, atm_obj=atm0)
+    ref = bmca.mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True)
+    for key in ('extinction', 'cer'):
+        cld0.lay[key]['data'] = pin_array(np.asarray(cld0.lay[key]['data'], dtype=np.float32))     # plain memory without a GPU
+    dev = bmca.mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True, device_props=True)
+    assert np.shares_memory(dev.nml['Atm_extp3d']['data'], cld0.lay['extinction']['data'])
+    assert np.shares_memory(dev.cer3d, cld0.lay['cer']['data'])
+    for key in ('Atm_extp3d', 'Atm_omgp3d', 'Atm_apfp3d', 'Atm_abst3d', 'Atm_tmpa3d'):
+        assert np.array_equal(np.asarray(dev.nml[key]['data']), np.asarray(ref.nml[key]['data'])), key
+    # a float64 / Fortran-ordered field is converted once instead of viewed
+    cld0.lay['extinction']['data'] = np.asfortranarray(cld0.lay['extinction']['data'].astype(np.float64))
+    dev2 = bmca.mca_atm_3d(cld_obj=cld0, atm_obj=atm0, pha_obj=pha0, quiet=True, device_props=True)
+    assert not np.shares_memory(dev2.nml['Atm_extp3d']['data'], cld0.lay['extinction']['data'])
+    assert dev2.nml['Atm_extp3d']['data'].dtype == np.float32 and np.array_equal(dev2.nml['Atm_extp3d']['data'], ref.nml['Atm_extp3d']['data'])
+    # scene hand-off
+    m = bmca.mcarats_ng(date=datetime.datetime(2017, 8, 13), atm_1ds=[bmca.mca_atm_1d(atm_obj=atm0, abs_obj=abs0)], atm_3ds=[dev], Ng=16,
+                        target='radiance', surface_albedo=0.03, sca=bmca.mca_sca(pha_obj=pha0), solar_zenith_angle=30.0,
+                        solar_azimuth_angle=45.0, fdir='tmp-data/devprops', Nrun=1, photons=1e4, weights=abs0.coef['weight']['data'],
+                        solver='3D', quiet=True, seed=1, dry_run=True)
+    st = m.scene.struct
+    assert st.cer3d and st.nref == 3 and not st.omg3d and not st.apf3d and st.layout3d == 1
