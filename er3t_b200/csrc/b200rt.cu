@@ -558,34 +558,41 @@ __device__ __forceinline__ int tally_col_m(const DevScene& S, const Photon& p) {
 }
 // tal_mode: 0 global atomics, 1 block-private shared tally, 2 warp-private shared tally
 // (updates that reach global memory are counted in the block's shared event counter; private ones at the flush)
+// SMT: the kernel may hold block-private tallies (plane-parallel / few-column scenes only, see transport_kernel); the other
+// kernels do not even contain the aggregation code -- the per-level kernel of config 5 is instruction-fetch bound and gained
+// 27 % when that never-executed code left it (profiles/README.md r02_t)
+template <bool SMT>
 __device__ __forceinline__ void flux_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int var, int lev, int col, float w) {
     const double v = double(w) * __ldg(t.fs + lev);
     const size_t idx = size_t(t.foff) + size_t(var * (S.nz + 1) + lev) * size_t(S.nx * S.ny) + size_t(col);
-    if (sm.ftal) tally_agg(sm.ftal + idx, v, sm.tal_mode);
+    if (SMT && sm.ftal) tally_agg(sm.ftal + idx, v, sm.tal_mode);
     else { tally_add(S.flux + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
+template <bool SMT>
 __device__ __forceinline__ void heat_add(const DevScene& S, const Smem& sm, const TallyCtx& t, int iz, int col, double dep) {
     const double v = dep * __ldg(t.fs + iz);
     const size_t idx = size_t(t.hoff) + size_t(iz) * size_t(S.nx * S.ny) + size_t(col);
-    if (sm.htal) tally_agg(sm.htal + idx, v, sm.tal_mode);
+    if (SMT && sm.htal) tally_agg(sm.htal + idx, v, sm.tal_mode);
     else { tally_add(S.heat + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
 
 // one flux / heating tally of a photon whose position is in metres (p.x, p.y)
+template <bool SMT>
 __device__ __forceinline__ void flux_tally(const DevScene& S, const Smem& sm, const Photon& p, int var, int lev) {
     const TallyCtx t = tally_ctx(S, p.job);
-    flux_add(S, sm, t, var, lev, tally_col_m(S, p), p.w);
+    flux_add<SMT>(S, sm, t, var, lev, tally_col_m(S, p), p.w);
 }
+template <bool SMT>
 __device__ __forceinline__ void heat_tally(const DevScene& S, const Smem& sm, const Photon& p, int iz, double dep) {
     const TallyCtx t = tally_ctx(S, p.job);
-    heat_add(S, sm, t, iz, tally_col_m(S, p), dep);
+    heat_add<SMT>(S, sm, t, iz, tally_col_m(S, p), dep);
 }
-// radiance tally (idx: position inside the whole radiance tally).  The block-private copy exists in the per-level (PL)
-// kernels only -- tiny sensors belong to plane-parallel / few-column scenes, which the host routes there -- so that the
-// radiance kernels of the large 3-D scenes carry neither the branch nor the aggregation code.
-template <bool PL>
+// radiance tally (idx: position inside the whole radiance tally).  The block-private copy exists in the per-level kernels
+// of plane-parallel / few-column scenes only (SMT) -- tiny sensors belong to such scenes, which the host routes there -- so
+// that the kernels of the large 3-D scenes carry neither the branch nor the aggregation code.
+template <bool SMT>
 __device__ __forceinline__ void rad_add(const DevScene& S, const Smem& sm, size_t idx, double v) {
-    if (PL && sm.rtal) tally_agg(sm.rtal + idx, v, sm.tal_mode);
+    if (SMT && sm.rtal) tally_agg(sm.rtal + idx, v, sm.tal_mode);
     else { tally_add(S.rad + idx, v); CNT_ADD(CNT_TALLY, 1u); }
 }
 
@@ -766,7 +773,7 @@ __device__ __forceinline__ float le_tau(const DevScene& S, const Smem& sm, const
 }
 
 // deposit one local-estimate contribution (fw = weight x angular density toward the sensor, 1/sr)
-template <bool PL>
+template <bool SMT>
 __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, const DevSensor& se, const Photon& p, float fw,
                                            int fx, int fy, float s3) {
     const float tau = le_tau(S, sm, se, p, fx, fy, s3);
@@ -782,7 +789,7 @@ __device__ __forceinline__ void le_deposit(const DevScene& S, const Smem& sm, co
         py = min(se.nyr - 1, max(0, int(yr * S.inv_Ly * float(se.nyr))));
     }
     const DevJob& J = S.jobs[p.job];
-    rad_add<PL>(S, sm, size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
+    rad_add<SMT>(S, sm, size_t(J.slab) * S.rad_slab + se.off + py * se.nxr + px, double(contrib) * J.rad_fac * se.npix);
     CNT_ADD(CNT_LE, 1u);
 }
 
@@ -897,6 +904,7 @@ __device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, c
 // With NP >= 96 some queue always holds a full warp of work, so the phases run at (close to) 32 active lanes instead of
 // the ~11 a one-photon-per-lane loop reaches (profiles/README.md).  Nothing in the pool is shared between warps: the
 // only synchronisation is __syncwarp.
+// RAD: radiance sensors present (false only in per-level kernels of pure flux / heating runs: no local-estimate code).
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
 // UZ (per-level kernels): the tight 1-D layer step is compiled in (plane-parallel and few-column scenes).
@@ -904,9 +912,10 @@ __device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, c
 //     slab: the fine slab of a photon that left a box sideways follows from its height, and the layer search for unequal
 //     layers is not part of the flight loop at all (the other kernels keep both, decided at run time).  Measured on config 2: the ~35 never-executed instructions of that search cost 3.4 % (the loop is
 //     instruction-fetch sensitive, profiles/README.md r02_f), hence a template parameter instead of a run-time test.
-template <bool PL, bool FZ, int NP, bool CAM, bool UZ>
+template <bool PL, bool FZ, int NP, bool CAM, bool UZ, bool RAD>
 __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
+    constexpr bool SMT = PL && UZ;      // block-private tallies exist only in the kernels of plane-parallel / few-column scenes
     Smem sm;
     float* pool;
     unsigned short *qD, *qF, *qE, *qC, *qS;
@@ -921,7 +930,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         double* acc_atm = acc + 4 * 32;
         double* tal = acc_atm + blockDim.x;
         // private tallies: one copy per block (shared atomics) or one per warp (tal_per_warp)
-        const int ntal1 = PL ? S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem : 0;
+        const int ntal1 = SMT ? S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem : 0;
         const int ntal = ntal1 * (S.tal_per_warp ? int(blockDim.x >> 5) : 1);
         unsigned* cnt = reinterpret_cast<unsigned*>(tal + ntal);
         float* q = reinterpret_cast<float*>(cnt + 8 * 32);
@@ -962,10 +971,10 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
         for (int i = threadIdx.x; i < ntal; i += blockDim.x) tal[i] = 0.0;
         {
             double* mine = tal + (S.tal_per_warp ? warp * ntal1 : 0);
-            const int nf = PL ? S.ntal_flux_smem : 0, nh = PL ? S.ntal_heat_smem : 0;
+            const int nf = SMT ? S.ntal_flux_smem : 0, nh = SMT ? S.ntal_heat_smem : 0;
             sm.ftal = nf > 0 ? mine : nullptr;
             sm.htal = nh > 0 ? mine + nf : nullptr;
-            sm.rtal = (PL && S.ntal_rad_smem > 0) ? mine + nf + nh : nullptr;
+            sm.rtal = (SMT && S.ntal_rad_smem > 0) ? mine + nf + nh : nullptr;
             sm.tal_mode = S.tal_per_warp ? 2 : 1;
         }
         for (int i = (threadIdx.x & 31); i < NP; i += 32) qD[i] = (unsigned short)i;
@@ -978,7 +987,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool want_flux = PL && (S.target & B200RT_TARGET_FLUX) != 0;
-    const bool want_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
+    const bool want_rad = RAD && (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
     const bool want_heat = PL && (S.target & B200RT_TARGET_HEATING) != 0;
     const int nxy = S.nx * S.ny;
 
@@ -1067,7 +1076,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                 }
                 p.tau = -__logf(v.x);
                 CNT_ADD(CNT_PHOT, 1u);
-                if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
+                if (want_flux) { flux_tally<SMT>(S, sm, p, 0, S.nz); flux_tally<SMT>(S, sm, p, 1, S.nz); }
                 pool_store<NP>(pool, slot, p, S.inv_Sx, S.inv_Sy);
             }
             QPUSH(qF, nF, born, slot);
@@ -1137,7 +1146,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         if (p.flags & FL_ABS) {
                             const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
                             ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                            if (want_heat) heat_add(S, sm, tcf, p.is, tally_col_u(S, ux, uy), double(p.w) - double(wn));
+                            if (want_heat) heat_add<SMT>(S, sm, tcf, p.is, tally_col_u(S, ux, uy), double(p.w) - double(wn));
                             p.w = wn;
                         }
                         p.leg += dmove;
@@ -1159,8 +1168,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                             p.flags &= ~FL_STALE;
                             if (want_flux) {
                                 const int col = tally_col_u(S, ux, uy);
-                                if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tcf, 0, p.is, col, p.w);
-                                flux_add(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
+                                if (!upz && (p.flags & FL_DIRECT)) flux_add<SMT>(S, sm, tcf, 0, p.is, col, p.w);
+                                flux_add<SMT>(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
                             }
                             const int nis = upz ? p.is + 1 : p.is - 1;
                             if (nis >= S.nslab_z) ev = EV_ESC;
@@ -1197,12 +1206,18 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     const bool empty = mj < 0.0f;                       // 1-D slabs count as empty
                     // empty boxes span the z groups glo ... ghi: the run of empty coarse cells encoded in the look-up
                     // (3-D block), or the slab's own group
-                    const int grp = (aw >> 16) & 0x7fff;
-                    const int code = (in3 && empty) ? __float2int_rn(-mj) - 1 : (grp | (grp << 12));
-                    const int glo = code & 0xfff, ghi = (code >> 12) & 0xfff;
-                    const float4 G = sm.grpA[glo], Gh = sm.grpA[ghi];  // zlo, zhi, 1-D majorant of the group, bits: slo | shi << 16
+                    // (per-level kernels: every slab is a single layer and its own group, coarse cells are fine cells and there
+                    // are no runs -- the slab record A is all a step needs, the group look-ups are compiled out)
+                    int glo = 0, ghi = 0;
+                    float4 G = A, Gh = A;                               // zlo, zhi, 1-D majorant of the group, bits: slo | shi << 16
+                    if (!PL) {
+                        const int grp = (aw >> 16) & 0x7fff;
+                        const int code = (in3 && empty) ? __float2int_rn(-mj) - 1 : (grp | (grp << 12));
+                        glo = code & 0xfff; ghi = (code >> 12) & 0xfff;
+                        G = sm.grpA[glo]; Gh = sm.grpA[ghi];
+                    }
                     // box in cell units: the fine cell, the enclosing coarse cell, or the whole domain (1-D slabs)
-                    const int mx = in3 ? (empty ? cmx : 0) : 0x3fffffff, my = in3 ? (empty ? cmy : 0) : 0x3fffffff;
+                    const int mx = in3 ? ((empty && !PL) ? cmx : 0) : 0x3fffffff, my = in3 ? ((empty && !PL) ? cmy : 0) : 0x3fffffff;
                     const int bxlo = p.cix & ~mx, bylo = p.ciy & ~my;
                     const int fxi = bxlo + ((mx + 1) & upmx), fyi = bylo + ((my + 1) & upmy);    // face index ahead
                     const float fxf = fminf(float(fxi), Lux), fyf = fminf(float(fyi), Luy);
@@ -1222,7 +1237,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         const float wn = p.w * __expf(-__ldg(S.job_abs + size_t(p.job) * S.nz + p.is) * dmove);
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
-                            heat_add(S, sm, tcf, p.is, frozen ? p.ciy * S.nx + p.cix : tally_col_u(S, ux, uy), double(p.w) - double(wn));
+                            heat_add<SMT>(S, sm, tcf, p.is, frozen ? p.ciy * S.nx + p.cix : tally_col_u(S, ux, uy), double(p.w) - double(wn));
                         }
                         p.w = wn;
                     }
@@ -1244,8 +1259,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     p.cix = xc ? cxn : cxi; ux = xc ? uxn : ux;
                     p.ciy = yc ? cyn : cyi; uy = yc ? uyn : uy;
 
-                    const int slo = empty ? (__float_as_int(G.w) & 0xffff) : p.is;
-                    const int shi = empty ? int(unsigned(__float_as_int(Gh.w)) >> 16) : p.is + 1;
+                    const int slo = (empty && !PL) ? (__float_as_int(G.w) & 0xffff) : p.is;
+                    const int shi = (empty && !PL) ? int(unsigned(__float_as_int(Gh.w)) >> 16) : p.is + 1;
                     int fl = p.flags;
                     if (mj >= 0.0f) fl &= ~FL_STALE;                              // only a non-empty cell resolves staleness
                     if ((xc || yc) && in3 && shi - slo > 1) fl |= FL_STALE;
@@ -1260,8 +1275,8 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         fl &= ~FL_STALE;
                         if (PL && want_flux) {
                             const int col = frozen ? p.ciy * S.nx + p.cix : tally_col_u(S, ux, uy);
-                            if (!upz && (p.flags & FL_DIRECT)) flux_add(S, sm, tcf, 0, p.is, col, p.w);
-                            flux_add(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
+                            if (!upz && (p.flags & FL_DIRECT)) flux_add<SMT>(S, sm, tcf, 0, p.is, col, p.w);
+                            flux_add<SMT>(S, sm, tcf, upz ? 2 : 1, upz ? p.is + 1 : p.is, col, p.w);
                         }
                         const int nis = upz ? shi : slo - 1;
                         if (nis >= S.nslab_z) ev = EV_ESC;
@@ -1370,7 +1385,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     const float wn = p.w * omg;
                     if (wn < p.w) {
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                        if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
+                        if (want_heat) heat_tally<SMT>(S, sm, p, izn, double(p.w) - double(wn));
                     }
                     p.w = wn;
                     p.order++; p.flags &= ~FL_DIRECT;
@@ -1473,7 +1488,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         CNT_ADD(CNT_VISIT, nv);
                         if (c > 0.0f) {
                             const DevJob& J = S.jobs[p.job];
-                            rad_add<PL>(S, sm, size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
+                            rad_add<SMT>(S, sm, size_t(J.slab) * S.rad_slab + se.off + pix, double(c * p.w) * J.rad_fac * se.npix);
                             CNT_ADD(CNT_LE, 1u);
                         }
                         continue;
@@ -1487,7 +1502,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                     } else {
                         f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, se.s) * se.s.z : 0.0f;
                     }
-                    if (f > 0.0f) le_deposit<PL>(S, sm, se, p, f * p.w, fx, fy, s3);
+                    if (f > 0.0f) le_deposit<SMT>(S, sm, se, p, f * p.w, fx, fy, s3);
                 }
             }
 
@@ -1511,7 +1526,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             }
             p.d = newd;
             if (evk == EV_SFC) {
-                if (want_flux) flux_tally(S, sm, p, 2, 0);
+                if (want_flux) flux_tally<SMT>(S, sm, p, 2, 0);
                 if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && (p.flags & FL_FROZEN))) {
                     p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                     p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
@@ -1541,7 +1556,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 #undef QPUSH_DEAD
 
     // ---- flush the block-private tallies (one global atomic per non-zero entry and block)
-    if (PL && (sm.ftal || sm.htal || sm.rtal)) {
+    if (SMT && (sm.ftal || sm.htal || sm.rtal)) {
         __syncthreads();
         const int nf = sm.ftal ? S.ntal_flux_smem : 0, nh = sm.htal ? S.ntal_heat_smem : 0, nr = S.ntal_rad_smem;
         const int ntal1 = nf + nh + nr;
@@ -1603,25 +1618,29 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 
 typedef void (*transport_fn)(const DevScene);
 template <int NP>
-static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz) {
+static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz, bool rad) {
     // CAM (all-sky camera sensors present) is its own specialisation: the camera's local estimate is a large cold path
     // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false).
-    // UZ only matters to the kernels that do not tally every level (the per-level ones use single-layer cells).
+    // UZ: see the kernel.  RAD = false exists for the per-level kernels only: a pure flux / heating run carries no
+    // local-estimate code at all (those kernels are instruction-fetch bound).
     if (pl) {
-        // (per-level kernels: the last flag compiles the tight 1-D layer step in -- plane-parallel / few-column scenes)
-        if (cam) return transport_kernel<true, false, NP, true, false>;
-        if (fz) return uz ? transport_kernel<true, true, NP, false, true> : transport_kernel<true, true, NP, false, false>;
-        return uz ? transport_kernel<true, false, NP, false, true> : transport_kernel<true, false, NP, false, false>;
+        if (cam) return transport_kernel<true, false, NP, true, false, true>;
+        if (rad) {
+            if (fz) return uz ? transport_kernel<true, true, NP, false, true, true> : transport_kernel<true, true, NP, false, false, true>;
+            return uz ? transport_kernel<true, false, NP, false, true, true> : transport_kernel<true, false, NP, false, false, true>;
+        }
+        if (fz) return uz ? transport_kernel<true, true, NP, false, true, false> : transport_kernel<true, true, NP, false, false, false>;
+        return uz ? transport_kernel<true, false, NP, false, true, false> : transport_kernel<true, false, NP, false, false, false>;
     }
-    if (cam) return uz ? transport_kernel<false, false, NP, true, true> : transport_kernel<false, false, NP, true, false>;
-    if (fz) return uz ? transport_kernel<false, true, NP, false, true> : transport_kernel<false, true, NP, false, false>;
-    return uz ? transport_kernel<false, false, NP, false, true> : transport_kernel<false, false, NP, false, false>;
+    if (cam) return uz ? transport_kernel<false, false, NP, true, true, true> : transport_kernel<false, false, NP, true, false, true>;
+    if (fz) return uz ? transport_kernel<false, true, NP, false, true, true> : transport_kernel<false, true, NP, false, false, true>;
+    return uz ? transport_kernel<false, false, NP, false, true, true> : transport_kernel<false, false, NP, false, false, true>;
 }
-static transport_fn pick_transport(bool pl, bool fz, bool cam, bool uz, int np) {
+static transport_fn pick_transport(bool pl, bool fz, bool cam, bool uz, bool rad, int np) {
     switch (np) {
-        case 64: return pick_transport_np<64>(pl, fz, cam, uz);
-        case 128: return pick_transport_np<128>(pl, fz, cam, uz);
-        default: return pick_transport_np<96>(pl, fz, cam, uz);
+        case 64: return pick_transport_np<64>(pl, fz, cam, uz, rad);
+        case 128: return pick_transport_np<128>(pl, fz, cam, uz, rad);
+        default: return pick_transport_np<96>(pl, fz, cam, uz, rad);
     }
 }
 
@@ -2239,7 +2258,7 @@ int b200rt_upload_scene(void* handle, const b200rt_scene* sc, const b200rt_optio
     // (smem_tally: < 0 off; 0 auto = one copy per block, warp-aggregated shared atomics; 2 = one copy per warp when that
     // fits 24 KB, plain read-modify-write after the aggregation)
     S.ntal_flux_smem = 0; S.ntal_heat_smem = 0; S.ntal_rad_smem = 0; S.tal_per_warp = 0;
-    if (opt->smem_tally >= 0 && per_level) {
+    if (opt->smem_tally >= 0 && per_level && (nz3 <= 0 || size_t(sc->nx) * sc->ny <= 64)) {      // the scenes whose kernels hold private tallies
         // two blocks per SM must still fit (pools of 96 slots per warp + tables + accumulators + the private tallies)
         auto fits2 = [&](size_t ntal) {
             const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(RT_TPB) * 8 + size_t(RT_TPB / 32) * size_t(POOL_WORDS(96)) * 4 + 8 * ntal;
@@ -2381,7 +2400,8 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     int bps = 0;
     // UZ kernels: equally thick 3-D layers with runs (S.uz_ok) -- or no 3-D block at all (the layer search is dead code then)
     const bool k_uz = H->k_pl ? (S.nz3 <= 0 || size_t(S.nx) * S.ny <= 64) : ((S.uz_ok != 0 && H->cmz == 1) || S.nz3 <= 0);
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, k_uz, np);
+    const bool k_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, k_uz, k_rad, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
