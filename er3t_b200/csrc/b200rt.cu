@@ -905,6 +905,7 @@ __device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, c
 // the ~11 a one-photon-per-lane loop reaches (profiles/README.md).  Nothing in the pool is shared between warps: the
 // only synchronisation is __syncwarp.
 // RAD: radiance sensors present (false only in per-level kernels of pure flux / heating runs: no local-estimate code).
+// NO3: no 3-D block at all (plane-parallel flux runs, config 1): neither the generic cell step nor the voxel look-ups exist.
 // PL: flux / heating target (every level crossing is tallied, cells are single layers, absorption applied per step).
 // FZ: column-frozen photons may occur (IPA and partial-3D solver modes).
 // UZ (per-level kernels): the tight 1-D layer step is compiled in (plane-parallel and few-column scenes).
@@ -912,7 +913,7 @@ __device__ __noinline__ float2 pick_component3(const float* __restrict__ ext3, c
 //     slab: the fine slab of a photon that left a box sideways follows from its height, and the layer search for unequal
 //     layers is not part of the flight loop at all (the other kernels keep both, decided at run time).  Measured on config 2: the ~35 never-executed instructions of that search cost 3.4 % (the loop is
 //     instruction-fetch sensitive, profiles/README.md r02_f), hence a template parameter instead of a run-time test.
-template <bool PL, bool FZ, int NP, bool CAM, bool UZ, bool RAD>
+template <bool PL, bool FZ, int NP, bool CAM, bool UZ, bool RAD, bool NO3>
 __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid_constant__ DevScene S) {
     extern __shared__ float4 smem_f4[];
     constexpr bool SMT = PL && UZ;      // block-private tallies exist only in the kernels of plane-parallel / few-column scenes
@@ -1178,7 +1179,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
                         }
                     }
                 }
-                if (have && ev == EV_NONE && !plane) {
+                if (!(NO3 && PL && UZ) && have && ev == EV_NONE && !plane) {
                     if (!PL && (UZ || S.uz_ok) && (p.flags & FL_STALE)) {
                         // left a box of several fine slabs sideways: the slab follows from the height
                         p.is = S.uz_s0 + min(S.ncz - 1, max(0, __float2int_rd((p.z - S.uz_z0) * S.uz_inv)));
@@ -1323,7 +1324,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             } else if (ev == EV_TENT) {
                 const bool frozen = FZ && (p.flags & FL_FROZEN);
                 const bool ev_empty = (p.flags & FL_EMPTY) != 0;
-                const bool ev_in3 = (p.flags & FL_IN3) != 0;
+                const bool ev_in3 = !NO3 && (p.flags & FL_IN3) != 0;
                 float4 u;
                 RNG4(u);
                 {
@@ -1429,7 +1430,7 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
             if (evk == EV_COLL) {
                 // ---- hand-over record of the tentative phase (pool_store_accept)
                 apf = p.leg; u.z = p.za; u.w = c_uw; s3 = p.M;
-                const bool ev_in3 = (p.flags & FL_IN3) != 0;
+                const bool ev_in3 = !NO3 && (p.flags & FL_IN3) != 0;
                 if (ev_in3) {
                     if (FZ && (p.flags & FL_FROZEN)) { fx = p.cix; fy = p.ciy; }
                     else {
@@ -1618,29 +1619,30 @@ __global__ void __launch_bounds__(RT_TPB, RT_MINB) transport_kernel(const __grid
 
 typedef void (*transport_fn)(const DevScene);
 template <int NP>
-static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz, bool rad) {
+static transport_fn pick_transport_np(bool pl, bool fz, bool cam, bool uz, bool rad, bool no3) {
     // CAM (all-sky camera sensors present) is its own specialisation: the camera's local estimate is a large cold path
     // whose register pressure must not tax the satellite-view kernels; it needs the 3-D solver (FZ = false).
     // UZ: see the kernel.  RAD = false exists for the per-level kernels only: a pure flux / heating run carries no
     // local-estimate code at all (those kernels are instruction-fetch bound).
     if (pl) {
-        if (cam) return transport_kernel<true, false, NP, true, false, true>;
+        if (cam) return transport_kernel<true, false, NP, true, false, true, false>;
         if (rad) {
-            if (fz) return uz ? transport_kernel<true, true, NP, false, true, true> : transport_kernel<true, true, NP, false, false, true>;
-            return uz ? transport_kernel<true, false, NP, false, true, true> : transport_kernel<true, false, NP, false, false, true>;
+            if (fz) return uz ? transport_kernel<true, true, NP, false, true, true, false> : transport_kernel<true, true, NP, false, false, true, false>;
+            return uz ? transport_kernel<true, false, NP, false, true, true, false> : transport_kernel<true, false, NP, false, false, true, false>;
         }
-        if (fz) return uz ? transport_kernel<true, true, NP, false, true, false> : transport_kernel<true, true, NP, false, false, false>;
-        return uz ? transport_kernel<true, false, NP, false, true, false> : transport_kernel<true, false, NP, false, false, false>;
+        if (fz) return uz ? transport_kernel<true, true, NP, false, true, false, false> : transport_kernel<true, true, NP, false, false, false, false>;
+        if (uz && no3) return transport_kernel<true, false, NP, false, true, false, true>;
+        return uz ? transport_kernel<true, false, NP, false, true, false, false> : transport_kernel<true, false, NP, false, false, false, false>;
     }
-    if (cam) return uz ? transport_kernel<false, false, NP, true, true, true> : transport_kernel<false, false, NP, true, false, true>;
-    if (fz) return uz ? transport_kernel<false, true, NP, false, true, true> : transport_kernel<false, true, NP, false, false, true>;
-    return uz ? transport_kernel<false, false, NP, false, true, true> : transport_kernel<false, false, NP, false, false, true>;
+    if (cam) return uz ? transport_kernel<false, false, NP, true, true, true, false> : transport_kernel<false, false, NP, true, false, true, false>;
+    if (fz) return uz ? transport_kernel<false, true, NP, false, true, true, false> : transport_kernel<false, true, NP, false, false, true, false>;
+    return uz ? transport_kernel<false, false, NP, false, true, true, false> : transport_kernel<false, false, NP, false, false, true, false>;
 }
-static transport_fn pick_transport(bool pl, bool fz, bool cam, bool uz, bool rad, int np) {
+static transport_fn pick_transport(bool pl, bool fz, bool cam, bool uz, bool rad, bool no3, int np) {
     switch (np) {
-        case 64: return pick_transport_np<64>(pl, fz, cam, uz, rad);
-        case 128: return pick_transport_np<128>(pl, fz, cam, uz, rad);
-        default: return pick_transport_np<96>(pl, fz, cam, uz, rad);
+        case 64: return pick_transport_np<64>(pl, fz, cam, uz, rad, no3);
+        case 128: return pick_transport_np<128>(pl, fz, cam, uz, rad, no3);
+        default: return pick_transport_np<96>(pl, fz, cam, uz, rad, no3);
     }
 }
 
@@ -2401,7 +2403,7 @@ int b200rt_run(void* handle, const b200rt_job* jobs, int njob, int accumulate, v
     // UZ kernels: equally thick 3-D layers with runs (S.uz_ok) -- or no 3-D block at all (the layer search is dead code then)
     const bool k_uz = H->k_pl ? (S.nz3 <= 0 || size_t(S.nx) * S.ny <= 64) : ((S.uz_ok != 0 && H->cmz == 1) || S.nz3 <= 0);
     const bool k_rad = (S.target & B200RT_TARGET_RADIANCE) != 0 && S.nrad > 0;
-    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, k_uz, k_rad, np);
+    transport_fn kern = pick_transport(H->k_pl, H->k_fz, H->k_cam, k_uz, k_rad, S.nz3 <= 0, np);
     const size_t smem = H->smem_tables + 32 * (4 * 8 + 8 * 4) + size_t(tpb) * 8 + size_t(tpb / 32) * size_t(POOL_WORDS(np)) * 4 +
                         8 * size_t(S.ntal_flux_smem + S.ntal_heat_smem + S.ntal_rad_smem) * size_t(S.tal_per_warp ? RT_TPB / 32 : 1);
     if (smem > 227 * 1024) return fail(H, B200RT_ERR_ARG, "photon pools + 1-D tables exceed shared memory; lower threads_per_block or pool_slots");
