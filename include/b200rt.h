@@ -160,8 +160,10 @@ typedef struct b200rt_options {
     int32_t iso_max;              /* Pho_iso_max: max scattering order sampled (0 = 1e6)       */
     int32_t threads_per_block;    /* 0 = auto                                                  */
     int32_t blocks_per_sm;        /* 0 = auto                                                  */
-    int32_t smem_tally;           /* block-private flux / heating tallies in shared memory when the whole tally is small
-                                     (<= 2048 doubles): 0 = auto (on), -1 = off (global atomics only)               */
+    int32_t smem_tally;           /* block-private tallies in shared memory for plane-parallel and few-column (<= 64 columns)
+                                     scenes whose whole flux + heating tally is <= 2048 doubles (radiance: <= 512): lanes of a
+                                     warp that hit the same address are summed first, one flush per block.  0 = auto (on),
+                                     -1 = off (global atomics only), 2 = additionally one private copy per warp           */
     int32_t kernel;               /* transport kernel: 0 = auto (8), 8 = every warp runs every phase on its own photon pool,
                                      9 = experiment: role-specialised warps + block-level pool (only in builds made with
                                      -DB200RT_WITH_V9; measured slower)                                 */
