@@ -1,5 +1,9 @@
 // transport_v9.cuh -- role-specialised photon transport (included by b200rt.cu after the shared helpers).
 //
+// EXPERIMENT, measured slower than the per-warp-pool kernel in every variant (profiles/ab_v9_r02.txt);
+// built only with -DB200RT_WITH_V9.  Kept compiling against the current helpers (tallies always take the global path
+// here); its GPU validation dates from commit ebb7d38.
+//
 // One block per SM.  The photon pool belongs to the BLOCK (NPB slots, structure of arrays in shared memory) and the
 // warps are specialised:
 //   geometry warps (the first V9_NWF warps, V9_RF registers each after `setmaxnreg.dec`): the flight phase only --
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                         ACC_ADD(ACC_ATM, double(p.w) - double(wn));
                         if (want_heat) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            heat_tally(S, sm, p, p.is, double(p.w) - double(wn));
+                            heat_tally<false>(S, sm, p, p.is, double(p.w) - double(wn));
                         }
                         p.w = wn;
                     }
@@ -370,10 +374,10 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                         fl &= ~FL_STALE;
                         if (PL && want_flux) {
                             p.x = ux * S.Sx; p.y = uy * S.Sy;
-                            if (upz) flux_tally(S, sm, p, 2, p.is + 1);
+                            if (upz) flux_tally<false>(S, sm, p, 2, p.is + 1);
                             else {
-                                if (p.flags & FL_DIRECT) flux_tally(S, sm, p, 0, p.is);
-                                flux_tally(S, sm, p, 1, p.is);
+                                if (p.flags & FL_DIRECT) flux_tally<false>(S, sm, p, 0, p.is);
+                                flux_tally<false>(S, sm, p, 1, p.is);
                             }
                         }
                         const int nis = upz ? shi : slo - 1;
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                     }
                     p.tau = -__logf(v.x);
                     CNT_ADD(CNT_PHOT, 1u);
-                    if (want_flux) { flux_tally(S, sm, p, 0, S.nz); flux_tally(S, sm, p, 1, S.nz); }
+                    if (want_flux) { flux_tally<false>(S, sm, p, 0, S.nz); flux_tally<false>(S, sm, p, 1, S.nz); }
                     pool_store<NPB>(pool, slot, p, S.inv_Sx, S.inv_Sy);
                 }
                 v9_fence();
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                         const float wn = p.w * omg;
                         if (wn < p.w) {
                             ACC_ADD(ACC_ATM, double(p.w) - double(wn));
-                            if (want_heat) heat_tally(S, sm, p, izn, double(p.w) - double(wn));
+                            if (want_heat) heat_tally<false>(S, sm, p, izn, double(p.w) - double(wn));
                         }
                         p.w = wn;
                         p.order++; p.flags &= ~FL_DIRECT;
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                         } else {
                             f = se.s.z > 0.0f ? brdf_eval(sfc_type, prm[0], prm[1], prm[2], prm[3], prm[4], wi, se.s) * se.s.z : 0.0f;
                         }
-                        if (f > 0.0f) le_deposit(S, sm, se, p, f * p.w, fx, fy, s3);
+                        if (f > 0.0f) le_deposit<false>(S, sm, se, p, f * p.w, fx, fy, s3);
                     }
                 }
 
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(V9_NT, 1) transport_v9(const __grid_constant__
                 }
                 p.d = newd;
                 if (evk == EV_SFC) {
-                    if (want_flux) flux_tally(S, sm, p, 2, 0);
+                    if (want_flux) flux_tally<false>(S, sm, p, 2, 0);
                     if (S.nz3 > 0 && S.iz0 == 0 && !(FZ && (p.flags & FL_FROZEN))) {
                         p.cix = min(S.ncx - 1, max(0, int(p.x * S.inv_Sx)));
                         p.ciy = min(S.ncy - 1, max(0, int(p.y * S.inv_Sy)));
