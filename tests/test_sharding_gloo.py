@@ -57,3 +57,20 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
     assert int(got['photons']) == 2 * 20001
     assert np.allclose(got['rad'], ref['rad'], rtol=1e-10, atol=1e-14)
     assert np.allclose(got['flux'], ref['flux'], rtol=1e-10, atol=1e-14)
+
+
+def test_lpt_assignment_of_whole_calls():
+    """tools/c4_sweep.py hands whole mcarats_ng calls (wavelengths) to ranks longest-first -- the idea of the reference's
+    `rearrange_jobs` (er3t/rtm/mca/mca_run.py:184-230) applied to calls: every call lands on exactly one rank and the
+    heaviest rank carries at most the lightest one's load plus one call."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tools'))
+    from c4_sweep import lpt_assign
+    rng = np.random.default_rng(4)
+    for world in (1, 2, 3, 8):
+        costs = list(rng.uniform(1.0, 5.0, 11))
+        parts = lpt_assign(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs) + 1e-12
+    assert lpt_assign([1.0] * 8, 8) == [[i] for i in range(8)]
